@@ -1,0 +1,100 @@
+/* mt_b200.h — C ABI of libmt_b200.so: the B200 (sm_100a) kernels behind Meta-Transformer's shared encoder path.
+ *
+ * The reference has NO native boundary on this path: it runs timm's Block / Attention / Mlp and the Data2Seq
+ * tokenizers as eager PyTorch (README.md:116-149).  Each entry point below replaces the torch.nn.functional
+ * calls of one reference span (cited per function; in-tree verbatim copies of the timm code are used for
+ * line numbers because timm itself is a pip dependency that is not vendored).
+ *
+ * Conventions
+ *  - plain C types only; device pointers are `void*` / typed pointers to DEVICE memory unless stated otherwise;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); nothing here synchronises the host;
+ *  - the caller owns every buffer (activations, outputs, workspaces); the library never allocates on the hot path;
+ *  - every function returns 0 (MT_OK) or a negative mt_status; mt_last_error() gives a thread-local message;
+ *  - bf16 tensors are row-major with the feature dimension contiguous; all pointers 16-byte aligned.
+ */
+#ifndef MT_B200_H_
+#define MT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  MT_OK = 0,
+  MT_ERR_BAD_SHAPE = -1,
+  MT_ERR_BAD_DTYPE = -2,
+  MT_ERR_BAD_ALIGN = -3,
+  MT_ERR_UNSUPPORTED = -4,
+  MT_ERR_CUDA = -5
+} mt_status;
+
+typedef enum { MT_DT_BF16 = 0, MT_DT_F32 = 1, MT_DT_F16 = 2 } mt_dtype;
+
+/* ---- library / device ---- */
+int mt_version(void);                 /* MAJOR*10000 + MINOR*100 + PATCH */
+const char* mt_last_error(void);      /* thread-local, never NULL */
+int mt_device_ok(int device);         /* 0 if `device` is compute capability 10.x (B200), else MT_ERR_UNSUPPORTED */
+
+/* ---- E3/E5/E6: Linear (+bias) (+GELU) (+residual)  --------------------------------------------------------
+ * y[M,N] = act(x[M,K] @ w[N,K]^T + bias[N]) (+ residual[M,N]);  x,w,residual,y bf16; bias fp32 (may be NULL).
+ * act: 0 = identity, 1 = exact-erf GELU (nn.GELU()).  cta_group: 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs.
+ * Replaces F.linear at PointCloud/openpoints/models/layers/attention.py:28 (qkv), :36 (proj) and
+ * mlp.py:30-33 (fc1, act, fc2), plus the residual adds of Block.forward (attention.py:56-57).           */
+int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                 int M, int N, int K, int act, int cta_group, void* stream);
+
+/* ---- E2: LayerNorm over the last dim, fp32 statistics, biased variance -------------------------------------
+ * y[M,d] (bf16) = (x - mean) * rsqrt(var + eps) * gamma + beta;  x bf16 or fp32 (x_dtype), gamma/beta fp32.
+ * Replaces norm1 / norm2 = nn.LayerNorm(d) of Block (attention.py:46,50; eps 1e-5 per README.md:131).       */
+int mt_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
+                 int M, int d, float eps, void* stream);
+
+/* ---- E4: softmax attention core -----------------------------------------------------------------------------
+ * qkv: bf16 [B, N, 3, H, dh] (the packed output of the qkv Linear, attention.py:28), out: bf16 [B, N, H*dh].
+ * out[b,n,h,:] = softmax_j(scale * q[b,n,h]·k[b,j,h]) · v[b,j,h]   (attention.py:31-35, no mask, no dropout).
+ * dh must be 64.                                                                                             */
+int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
+
+/* ---- T1/T2/T3: patch / spectrogram / tubelet embedding -----------------------------------------------------
+ * Non-overlapping or strided Conv{2,3}d as im2row + GEMM.
+ * mt_im2row: x [B, C, T, H, W] (x_dtype fp32 or bf16; T = kt = 1 for 2-D) -> rows bf16 [B*Tp*Hp*Wp, C*kt*kh*kw]
+ * in the K-order (c, kt, kh, kw) of conv.weight.view(d, -1); token order (t, h, w) row-major
+ * (Data2Seq/Image.py:16,26; Video/models/modeling_finetune.py:285-297; Audio/src/models/ast_models.py:86).   */
+int mt_im2row(const void* x, int x_dtype, void* rows, int B, int C, int T, int H, int W,
+              int kt, int kh, int kw, int st, int sh, int sw, void* stream);
+
+/* ---- dtype conversion helper (weights packing, fp32 activations at the boundary) ---- */
+int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
+
+/* ---- E0/E1: whole-encoder driver ---------------------------------------------------------------------------
+ * nn.Sequential(*[Block(dim, heads, mlp_ratio, qkv_bias=True) for _ in range(depth)]) (README.md:125-147).
+ * Weights are borrowed device pointers (bf16 matrices, fp32 vectors) that must outlive the handle.          */
+typedef struct mt_encoder mt_encoder;
+
+typedef struct {
+  const float* ln1_w; const float* ln1_b;      /* [d]            norm1.{weight,bias}      */
+  const void* qkv_w;  const float* qkv_b;      /* [3d,d] bf16, [3d] fp32 (NULL = no bias) */
+  const void* proj_w; const float* proj_b;     /* [d,d],  [d]    */
+  const float* ln2_w; const float* ln2_b;      /* [d]            norm2                    */
+  const void* fc1_w;  const float* fc1_b;      /* [hidden,d], [hidden] */
+  const void* fc2_w;  const float* fc2_b;      /* [d,hidden], [d]      */
+} mt_block_weights;
+
+int mt_encoder_create(mt_encoder** out, int dim, int heads, int hidden, int depth, float eps,
+                      const mt_block_weights* blocks /* [depth], host array of device pointers */);
+int mt_encoder_destroy(mt_encoder* enc);
+/* bytes of scratch needed for a (B, N) forward */
+int mt_encoder_workspace_bytes(const mt_encoder* enc, int B, int N, size_t* bytes);
+/* x, y: bf16 [B, N, dim] (y may alias x); workspace: device scratch of at least workspace_bytes */
+int mt_encoder_forward(mt_encoder* enc, const void* x, void* y, int B, int N,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* number of kernels one mt_encoder_forward launches (for accounting) */
+int mt_encoder_launches_per_forward(const mt_encoder* enc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MT_B200_H_ */

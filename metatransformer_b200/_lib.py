@@ -1,0 +1,94 @@
+"""ctypes binding of libmt_b200.so (the C ABI declared in include/mt_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception is raised.
+The product path never routes through PyTorch eager math or through oracle/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p, POINTER, Structure
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libmt_b200.so"
+
+MT_DT_BF16, MT_DT_F32, MT_DT_F16 = 0, 1, 2
+
+EXPORTED_SYMBOLS = (
+    "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_layernorm", "mt_attention_fwd",
+    "mt_im2row", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
+    "mt_encoder_forward", "mt_encoder_launches_per_forward",
+)
+
+
+class MtError(RuntimeError):
+    pass
+
+
+class BlockWeights(Structure):
+    """mirror of `mt_block_weights`"""
+    _fields_ = [
+        ("ln1_w", c_void_p), ("ln1_b", c_void_p),
+        ("qkv_w", c_void_p), ("qkv_b", c_void_p),
+        ("proj_w", c_void_p), ("proj_b", c_void_p),
+        ("ln2_w", c_void_p), ("ln2_b", c_void_p),
+        ("fc1_w", c_void_p), ("fc1_b", c_void_p),
+        ("fc2_w", c_void_p), ("fc2_b", c_void_p),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib: ctypes.CDLL) -> None:
+    lib.mt_version.restype = c_int
+    lib.mt_version.argtypes = []
+    lib.mt_last_error.restype = c_char_p
+    lib.mt_last_error.argtypes = []
+    lib.mt_device_ok.restype = c_int
+    lib.mt_device_ok.argtypes = [c_int]
+    lib.mt_gemm_bf16.restype = c_int
+    lib.mt_gemm_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p]
+    lib.mt_layernorm.restype = c_int
+    lib.mt_layernorm.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]
+    lib.mt_attention_fwd.restype = c_int
+    lib.mt_attention_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.mt_im2row.restype = c_int
+    lib.mt_im2row.argtypes = [c_void_p, c_int, c_void_p] + [c_int] * 11 + [c_void_p]
+    lib.mt_cast.restype = c_int
+    lib.mt_cast.argtypes = [c_void_p, c_int, c_void_p, c_int, c_size_t, c_void_p]
+    lib.mt_encoder_create.restype = c_int
+    lib.mt_encoder_create.argtypes = [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_float, POINTER(BlockWeights)]
+    lib.mt_encoder_destroy.restype = c_int
+    lib.mt_encoder_destroy.argtypes = [c_void_p]
+    lib.mt_encoder_workspace_bytes.restype = c_int
+    lib.mt_encoder_workspace_bytes.argtypes = [c_void_p, c_int, c_int, POINTER(c_size_t)]
+    lib.mt_encoder_forward.restype = c_int
+    lib.mt_encoder_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]
+    lib.mt_encoder_launches_per_forward.restype = c_int
+    lib.mt_encoder_launches_per_forward.argtypes = [c_void_p]
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the library; raise if it has not been built (`python -m metatransformer_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("MT_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise MtError(
+            f"{path} not found: the sm_100a extension has not been built. Run `python -m metatransformer_b200.build` "
+            "(needs nvcc). There is no CPU / eager fallback for this path.")
+    import torch  # noqa: F401  (loads torch's libcudart.so.12 first so both share one CUDA runtime instance)
+    lib = ctypes.CDLL(str(path), mode=ctypes.RTLD_GLOBAL)
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().mt_last_error().decode("utf-8", "replace")
+        raise MtError(f"{what} failed with status {rc}: {msg}")

@@ -1,0 +1,423 @@
+// mt_attention.cu — softmax attention core of timm's Attention.forward (E4 in SURVEY.md §8a):
+//   attn = (q @ k^T) * scale; attn = softmax(attn, -1); x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+//   (PointCloud/openpoints/models/layers/attention.py:31-35; Image/.../base/vit.py:108-112 is the same math).
+// The reference materialises the B*H*N*N score matrix; here S and P never leave the SM.
+//
+// Blackwell design (sm_100a only), head_dim = 64, no mask, no dropout:
+//   * q, k, v are read straight out of the packed (B, N, 3, H, 64) qkv buffer through one 4-D TMA descriptor
+//     (no permute / contiguous copies), output is written straight into (B, N, H*64) through a 4-D TMA store;
+//   * persistent CTAs; a work item is (batch, head, 256 query rows) = two 128-row query tiles that ping-pong:
+//     while the softmax warps of tile 0 work on S0, the tensor core computes S1 / P1·V, and vice versa;
+//   * S = Q·K^T and O += P·V are tcgen05.mma (bf16 in, fp32 accumulate) with S and O living in TMEM
+//     (S0,S1: 2 x 128 columns, O0,O1: 2 x 64 columns); V is consumed as an MN-major operand so no transpose;
+//   * online softmax in fp32 registers, one query row per thread (tcgen05.ld 32x32b), exp2 with the
+//     scale*log2(e) factor folded in; P goes back as bf16 through 128B-swizzled smem;
+//   * K/V tiles (128 keys) stream through 3-stage TMA rings shared by both query tiles.
+//
+// Warps (384 threads): 0-3 softmax tile 0, 4-7 softmax tile 1 (warp%4 = TMEM lane quarter), 8 = TMA loader,
+// 9 = MMA issuer + TMEM allocator, 10-11 idle (complete the third warpgroup for setmaxnreg).
+#include "mt_ptx.cuh"
+#include "mt_common.cuh"
+
+namespace mt {
+
+constexpr int kAtQT = 2;                    // query tiles per CTA
+constexpr int kAtBM = 128;                  // query rows per tile
+constexpr int kAtBN = 128;                  // keys per KV tile
+constexpr int kAtD = 64;                    // head dim
+constexpr int kAtStages = 3;
+constexpr int kAtThreads = 32 * (4 * kAtQT + 4);  // warps 10, 11 only pad the third warpgroup (setmaxnreg)
+constexpr int kAtTileBytes = 128 * 64 * 2;  // 16 KB: any 128 x 64 bf16 tile
+constexpr int kAtSmemQ = 0;
+constexpr int kAtSmemK = kAtSmemQ + kAtQT * kAtTileBytes;
+constexpr int kAtSmemV = kAtSmemK + kAtStages * kAtTileBytes;
+constexpr int kAtSmemP = kAtSmemV + kAtStages * kAtTileBytes;           // per q-tile: 2 chunks of 64 keys
+constexpr int kAtSmemBar = kAtSmemP + kAtQT * 2 * kAtTileBytes;
+// barriers: q_full[2] q_empty[2] k_full[3] k_empty[3] v_full[3] v_empty[3] s_full[2] s_empty[2] p_full[2] o_done[2]
+constexpr int kAtNumBars = 4 * kAtQT + 4 * kAtStages + 2 * kAtQT;
+constexpr int kAtSmemTmemPtr = kAtSmemBar + kAtNumBars * 8;
+constexpr int kAtSmemBytes = kAtSmemTmemPtr + 16 + 1024;
+constexpr int kAtTmemCols = 512;
+constexpr int kAtTmemS = 0;     // S_t at columns 128*t
+constexpr int kAtTmemO = 256;   // O_t at columns 256 + 64*t
+
+MT_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnParams {
+  int B, N, H;
+  int num_qp;        // ceil(N / 256)
+  int num_kv;        // ceil(N / 128)
+  int num_items;     // B * H * num_qp
+  float scale_log2;  // scale * log2(e)
+};
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
+                     const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bar0 = smem_base + kAtSmemBar;
+  auto q_full = [&](int t) { return bar0 + 8u * (0 + t); };
+  auto q_empty = [&](int t) { return bar0 + 8u * (2 + t); };
+  auto k_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (10 + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (13 + s); };
+  auto s_full = [&](int t) { return bar0 + 8u * (16 + t); };
+  auto s_empty = [&](int t) { return bar0 + 8u * (18 + t); };
+  auto p_full = [&](int t) { return bar0 + 8u * (20 + t); };
+  auto o_done = [&](int t) { return bar0 + 8u * (22 + t); };
+  const uint32_t tmem_ptr_addr = smem_base + kAtSmemTmemPtr;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kAtSmemTmemPtr);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_out);
+    for (int t = 0; t < kAtQT; ++t) {
+      mbar_init(q_full(t), 1);
+      mbar_init(q_empty(t), 1);
+      mbar_init(s_full(t), 1);
+      mbar_init(s_empty(t), 4);  // one arrive per softmax warp
+      mbar_init(p_full(t), 4);
+      mbar_init(o_done(t), 1);
+    }
+    for (int s = 0; s < kAtStages; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
+    }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 9) tmem_alloc<1>(tmem_ptr_addr, kAtTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int H = p.H;
+
+  // register re-distribution between warpgroups (compiled for 168/thread): the softmax warpgroups hold a whole
+  // 128-column score row per thread, the loader / MMA warpgroup needs almost nothing
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  if (warp == 8) {
+    // =============================== TMA loader =================================
+    if (lane == 0) {
+      int kst = 0; uint32_t kph = 0;
+      int vst = 0; uint32_t vph = 0;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int qp = item % p.num_qp;
+        const int bh = item / p.num_qp;
+        const int h = bh % H, b = bh / H;
+        for (int t = 0; t < kAtQT; ++t) {
+          mbar_wait(q_empty(t), (it & 1u) ^ 1u);
+          mbar_arrive_expect_tx(q_full(t), kAtTileBytes);
+          tma_load_4d(smem_base + kAtSmemQ + t * kAtTileBytes, &tm_qkv, q_full(t), 0, h, qp * 256 + t * 128, b,
+                      kEvictFirst);
+        }
+        for (int j = 0; j < p.num_kv; ++j) {
+          mbar_wait(k_empty(kst), kph ^ 1u);
+          mbar_arrive_expect_tx(k_full(kst), kAtTileBytes);
+          tma_load_4d(smem_base + kAtSmemK + kst * kAtTileBytes, &tm_qkv, k_full(kst), 0, H + h, j * kAtBN, b,
+                      kEvictLast);
+          if (++kst == kAtStages) { kst = 0; kph ^= 1u; }
+          mbar_wait(v_empty(vst), vph ^ 1u);
+          mbar_arrive_expect_tx(v_full(vst), kAtTileBytes);
+          tma_load_4d(smem_base + kAtSmemV + vst * kAtTileBytes, &tm_qkv, v_full(vst), 0, 2 * H + h, j * kAtBN, b,
+                      kEvictLast);
+          if (++vst == kAtStages) { vst = 0; vph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAtBM, kAtBN, 0, 0);   // S = Q K^T   (both K-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16(kAtBM, kAtD, 0, 1);    // O = P V     (V is MN-major)
+      int kst = 0; uint32_t kph = 0;
+      int vst = 0; uint32_t vph = 0;
+      uint32_t n_s[kAtQT] = {0, 0};  // S_t tiles issued so far
+      uint32_t n_p[kAtQT] = {0, 0};  // P_t tiles consumed so far
+      uint32_t it = 0;
+
+      auto issue_s = [&](int t, int kstage) {
+        // wait until the softmax warps pulled the previous S_t out of TMEM
+        mbar_wait(s_empty(t), (n_s[t] & 1u) ^ 1u);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc_sw128(smem_base + kAtSmemQ + t * kAtTileBytes);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_base + kAtSmemK + kstage * kAtTileBytes);
+#pragma unroll
+        for (int k = 0; k < kAtD / 16; ++k)
+          umma_f16_ss<1>(tmem_base + kAtTmemS + t * kAtBN, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s,
+                         k > 0 ? 1u : 0u);
+        umma_commit(s_full(t));
+        ++n_s[t];
+      };
+
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        // ---- prologue: S_t(0) for both query tiles ----
+        mbar_wait(k_full(kst), kph);
+#pragma unroll
+        for (int t = 0; t < kAtQT; ++t) {
+          mbar_wait(q_full(t), it & 1u);
+          tc_fence_after();
+          issue_s(t, kst);
+          if (p.num_kv == 1) umma_commit(q_empty(t));
+        }
+        umma_commit(k_empty(kst));
+        if (++kst == kAtStages) { kst = 0; kph ^= 1u; }
+
+        for (int j = 0; j < p.num_kv; ++j) {
+          const int valid = min(kAtBN, p.N - j * kAtBN);
+          const int ksteps = 2 * ((valid + 31) / 32);  // 16-key steps covering the valid 32-key chunks
+          const bool more = (j + 1 < p.num_kv);
+          mbar_wait(v_full(vst), vph);
+          if (more) mbar_wait(k_full(kst), kph);
+#pragma unroll
+          for (int t = 0; t < kAtQT; ++t) {
+            // ---- O_t (+)= P_t(j) V_j ----
+            mbar_wait(p_full(t), n_p[t] & 1u);
+            ++n_p[t];
+            tc_fence_after();
+            const uint32_t pbase = smem_base + kAtSmemP + t * 2 * kAtTileBytes;
+            const uint32_t vbase = smem_base + kAtSmemV + vst * kAtTileBytes;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(pbase + (k >> 2) * kAtTileBytes) + uint64_t(2 * (k & 3));
+              const uint64_t bdesc = make_smem_desc_sw128(vbase + k * 16 * 128);  // 16 keys = 16 rows of 128 B
+              umma_f16_ss<1>(tmem_base + kAtTmemO + t * kAtD, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(o_done(t));
+            if (t == kAtQT - 1) {
+              umma_commit(v_empty(vst));
+            }
+            // ---- S_t(j+1) ----
+            if (more) {
+              issue_s(t, kst);
+              if (j + 2 == p.num_kv) umma_commit(q_empty(t));  // last use of Q_t for this item
+              if (t == kAtQT - 1) umma_commit(k_empty(kst));
+            }
+          }
+          if (++vst == kAtStages) { vst = 0; vph ^= 1u; }
+          if (more) { if (++kst == kAtStages) { kst = 0; kph ^= 1u; } }
+        }
+      }
+    }
+  }
+  } else {
+    // =============================== softmax warps ==============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int t = warp >> 2;        // query tile
+    const int q = warp & 3;         // TMEM lane quarter
+    const int r_in_tile = 32 * q + lane;
+    const uint32_t lane_off = uint32_t(32 * q) << 16;
+    const uint32_t ts = tmem_base + lane_off + uint32_t(kAtTmemS + t * kAtBN);
+    const uint32_t to = tmem_base + lane_off + uint32_t(kAtTmemO + t * kAtD);
+    const uint32_t pbase = smem_base + kAtSmemP + t * 2 * kAtTileBytes;
+    const uint32_t prow = pbase + uint32_t(r_in_tile * 128);
+    const uint32_t swz = uint32_t(r_in_tile & 7);
+    uint32_t n_sf = 0, n_od = 0;
+    bool store_pending = false;
+    const float c = p.scale_log2;
+
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int qp = item % p.num_qp;
+      const int bh = item / p.num_qp;
+      const int h = bh % H, b = bh / H;
+      float m_run = -INFINITY;
+      float l_run = 0.f;
+
+      for (int j = 0; j < p.num_kv; ++j) {
+        const int valid = min(kAtBN, p.N - j * kAtBN);
+        const int nch = (valid + 31) >> 5;  // 32-key chunks that hold at least one valid key
+        const bool need_mask = (valid & 31) != 0;
+        mbar_wait(s_full(t), n_sf & 1u);
+        ++n_sf;
+        tc_fence_after();
+        uint32_t s[128];
+        tmem_ld_32x32b_x32_at<0>(ts, s);
+        if (nch > 1) tmem_ld_32x32b_x32_at<32>(ts + 32u, s);
+        if (nch > 2) tmem_ld_32x32b_x32_at<64>(ts + 64u, s);
+        if (nch > 3) tmem_ld_32x32b_x32_at<96>(ts + 96u, s);
+        tmem_wait_ld();
+        // S_t is in registers: the tensor core may overwrite it with the next tile's scores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(t));
+
+        // ---- running max ----
+        float m_tile = -INFINITY;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch < nch) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float v = __uint_as_float(s[32 * ch + i]);
+              if (need_mask && ch == nch - 1) {  // warp-uniform: only the last chunk can hold padded keys
+                v = (32 * ch + i < valid) ? v : -INFINITY;
+                s[32 * ch + i] = __float_as_uint(v);
+              }
+              m_tile = fmaxf(m_tile, v);
+            }
+          }
+        }
+        const float m_new = fmaxf(m_run, m_tile);
+        const float alpha = ex2_approx((m_run - m_new) * c);  // 0 on the first tile (m_run = -inf)
+        const float mc = m_new * c;
+        m_run = m_new;
+
+        // ---- P_t smem and O_t are busy until P_t(j-1)·V_(j-1) has finished.  S_t(j) was issued after that
+        //      MMA and tcgen05 ops retire in order, so this wait never actually blocks. ----
+        if (j > 0) {
+          mbar_wait(o_done(t), n_od & 1u);
+          ++n_od;
+          tc_fence_after();
+          // rescale the running output by alpha
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(to + uint32_t(32 * hh), o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(to + uint32_t(32 * hh), o);
+          }
+          tmem_wait_st();
+        }
+        if (store_pending) {
+          // the previous item's output tile was staged in this warp's rows of P_t
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          store_pending = false;
+        }
+        // ---- P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V) ----
+        float l_tile = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          if (ch < nch) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {  // four 16-byte groups (8 keys each) per 32-key chunk
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float e0 = ex2_approx(fmaf(__uint_as_float(s[32 * ch + 8 * g + 2 * i]), c, -mc));
+                const float e1 = ex2_approx(fmaf(__uint_as_float(s[32 * ch + 8 * g + 2 * i + 1]), c, -mc));
+                l_tile += e0 + e1;
+                pk[i] = pack_bf16x2(e0, e1);
+              }
+              const uint32_t chunk16 = uint32_t((ch & 1) * 4 + g);
+              const uint32_t addr = prow + uint32_t((ch >> 1) * kAtTileBytes) + ((chunk16 ^ swz) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                           "r"(pk[3])
+                           : "memory");
+            }
+          }
+        }
+        l_run = fmaf(l_run, alpha, l_tile);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(t));
+      }
+
+      // ---- epilogue: O_t / l -> bf16 -> staged in this warp's rows of P_t chunk 0 -> TMA store ----
+      mbar_wait(o_done(t), n_od & 1u);
+      ++n_od;
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      uint32_t ob[32];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(to + uint32_t(32 * hh), o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          ob[(32 * hh + i) >> 1] = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+      }
+      tc_fence_before();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t addr = prow + ((uint32_t(g) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ob[4 * g + 0]), "r"(ob[4 * g + 1]),
+                     "r"(ob[4 * g + 2]), "r"(ob[4 * g + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      const int row0 = qp * 256 + t * 128 + 32 * q;
+      if (lane == 0 && row0 < p.N) {
+        tma_store_4d(&tm_out, pbase + uint32_t(32 * q * 128), 0, h, row0, b);
+        tma_store_commit();
+      }
+      store_pending = true;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<1>(tmem_base, kAtTmemCols);
+}
+
+}  // namespace mt
+
+extern "C" int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(qkv && out, MT_ERR_BAD_SHAPE, "mt_attention_fwd: null pointer");
+  MT_REQUIRE(B > 0 && N > 0 && H > 0, MT_ERR_BAD_SHAPE, "mt_attention_fwd: B, N, H must be positive");
+  MT_REQUIRE(dh == 64, MT_ERR_UNSUPPORTED, "mt_attention_fwd: head_dim %d not supported (only 64)", dh);
+  MT_REQUIRE(scale > 0.f, MT_ERR_UNSUPPORTED, "mt_attention_fwd: scale must be positive");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, MT_ERR_BAD_ALIGN,
+             "mt_attention_fwd: pointers must be 16-byte aligned");
+  CUtensorMap tm_qkv, tm_out;
+  {
+    // (B, N, 3, H, 64) viewed as dims [64, 3H, N, B]
+    uint64_t dims[4] = {64, uint64_t(3 * H), uint64_t(N), uint64_t(B)};
+    uint64_t strides[3] = {64 * 2, uint64_t(3 * H) * 64 * 2, uint64_t(N) * 3 * H * 64 * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int rc = encode_tmap(&tm_qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, qkv, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    // (B, N, H, 64) viewed as dims [64, H, N, B]; one store = 32 query rows of one head
+    uint64_t dims[4] = {64, uint64_t(H), uint64_t(N), uint64_t(B)};
+    uint64_t strides[3] = {64 * 2, uint64_t(H) * 64 * 2, uint64_t(N) * H * 64 * 2};
+    uint32_t box[4] = {64, 1, 32, 1};
+    int rc = encode_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.B = B; p.N = N; p.H = H;
+  p.num_qp = ceil_div(N, 256);
+  p.num_kv = ceil_div(N, kAtBN);
+  p.num_items = B * H * p.num_qp;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  int grid = p.num_items < sms ? p.num_items : sms;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+    attr_set = true;
+  }
+  attention_fwd_kernel<<<unsigned(grid), kAtThreads, kAtSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm_qkv, tm_out,
+                                                                                                            p);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}

@@ -1,0 +1,163 @@
+// mt_capi.cu — library-level pieces of the C ABI: version, error string, device check, TMA descriptor
+// encoding via the driver entry point, dtype casts.
+#include "mt_ptx.cuh"
+#include "mt_common.cuh"
+#include <string.h>
+#include <cuda_fp16.h>
+
+namespace mt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", int(e), cudaGetErrorString(e), what);
+  return MT_ERR_CUDA;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+    else (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* gptr, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                CUtensorMapL2promotion promo) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver / no GPU?)");
+    return MT_ERR_CUDA;
+  }
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, dtype, cuuint32_t(rank), const_cast<void*>(gptr), gdims, gstr, gbox, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu x %llu, box %u x %u, ptr %p)", int(r),
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],
+              rank > 1 ? box[1] : 0, gptr);
+    return MT_ERR_CUDA;
+  }
+  return MT_OK;
+}
+
+int sm_count(int* out) {
+  static int cached[64] = {0};
+  int dev = 0;
+  MT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) {
+    *out = cached[dev];
+    return MT_OK;
+  }
+  int n = 0;
+  MT_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  *out = n;
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise cast (weight packing fp32 -> bf16, boundary conversions). Memory-bound, 16 B per thread-load.
+// ------------------------------------------------------------------------------------------------
+template <typename S>
+MT_DEVINL float to_f32(S v);
+template <> MT_DEVINL float to_f32<float>(float v) { return v; }
+template <> MT_DEVINL float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> MT_DEVINL float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename D>
+MT_DEVINL D from_f32(float v);
+template <> MT_DEVINL float from_f32<float>(float v) { return v; }
+template <> MT_DEVINL __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> MT_DEVINL __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      S s[4];
+      if constexpr (sizeof(S) == 4) *reinterpret_cast<uint4*>(s) = *reinterpret_cast<const uint4*>(src + i);
+      else *reinterpret_cast<uint2*>(s) = *reinterpret_cast<const uint2*>(src + i);
+      D d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = from_f32<D>(to_f32<S>(s[j]));
+      if constexpr (sizeof(D) == 4) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<uint4*>(d);
+      else *reinterpret_cast<uint2*>(dst + i) = *reinterpret_cast<uint2*>(d);
+    } else {
+      for (size_t j = i; j < n; ++j) dst[j] = from_f32<D>(to_f32<S>(src[j]));
+    }
+  }
+}
+
+template <typename S, typename D>
+static int launch_cast(const void* src, void* dst, size_t n, cudaStream_t s) {
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks > size_t(sms) * 16) blocks = size_t(sms) * 16;
+  if (blocks < 1) blocks = 1;
+  cast_kernel<S, D><<<unsigned(blocks), 256, 0, s>>>(reinterpret_cast<const S*>(src), reinterpret_cast<D*>(dst), n);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+}  // namespace mt
+
+extern "C" int mt_version(void) { return 100; }
+
+extern "C" const char* mt_last_error(void) { return mt::g_err; }
+
+extern "C" int mt_device_ok(int device) {
+  using namespace mt;
+  cudaDeviceProp prop;
+  MT_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  MT_REQUIRE(prop.major == 10, MT_ERR_UNSUPPORTED,
+             "device %d is compute capability %d.%d; libmt_b200 contains sm_100a code only", device, prop.major,
+             prop.minor);
+  return MT_OK;
+}
+
+extern "C" int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(src && dst, MT_ERR_BAD_SHAPE, "mt_cast: null pointer");
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_cast: pointers must be 16-byte aligned");
+  if (n == 0) return MT_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (src_dtype == MT_DT_F32 && dst_dtype == MT_DT_BF16) return launch_cast<float, __nv_bfloat16>(src, dst, n, s);
+  if (src_dtype == MT_DT_BF16 && dst_dtype == MT_DT_F32) return launch_cast<__nv_bfloat16, float>(src, dst, n, s);
+  if (src_dtype == MT_DT_F16 && dst_dtype == MT_DT_BF16) return launch_cast<__half, __nv_bfloat16>(src, dst, n, s);
+  if (src_dtype == MT_DT_BF16 && dst_dtype == MT_DT_F16) return launch_cast<__nv_bfloat16, __half>(src, dst, n, s);
+  if (src_dtype == MT_DT_F16 && dst_dtype == MT_DT_F32) return launch_cast<__half, float>(src, dst, n, s);
+  if (src_dtype == MT_DT_F32 && dst_dtype == MT_DT_F16) return launch_cast<float, __half>(src, dst, n, s);
+  set_error("mt_cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+  return MT_ERR_BAD_DTYPE;
+}

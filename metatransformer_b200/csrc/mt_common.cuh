@@ -1,0 +1,42 @@
+// mt_common.cuh — host-side helpers shared by the C-ABI translation units:
+// error reporting, driver-entry-point TMA descriptor encoding, launch helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/mt_b200.h"
+
+namespace mt {
+
+// thread-local last error message (returned by mt_last_error)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define MT_CHECK_CUDA(expr)                                   \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ::mt::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define MT_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      ::mt::set_error(__VA_ARGS__);  \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+// cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency,
+// so the library also loads on a box without a driver — required for the CPU-side symbol tests).
+// dims/strides are innermost-first; strides (bytes) are given for dims 1..rank-1.
+int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* gptr, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+
+int sm_count(int* out);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace mt

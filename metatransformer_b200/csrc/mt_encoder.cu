@@ -1,0 +1,110 @@
+// mt_encoder.cu — whole-encoder driver (E0/E1 in SURVEY.md §8a): the reference's
+//   encoder = nn.Sequential(*[Block(dim, num_heads, mlp_ratio=4., qkv_bias=True, norm_layer=nn.LayerNorm,
+//                                   act_layer=nn.GELU) for i in range(depth)])          (README.md:125-147)
+//   Block.forward: x = x + attn(norm1(x)); x = x + mlp(norm2(x))   (PointCloud/.../layers/attention.py:55-58)
+// run as 7 launches per Block on one stream with caller-provided scratch, instead of ~15 eager kernels:
+//   LN1 -> GEMM(qkv,+bias) -> attention -> GEMM(proj,+bias,+x) -> LN2 -> GEMM(fc1,+bias,GELU) -> GEMM(fc2,+bias,+x)
+#include "mt_common.cuh"
+#include <vector>
+#include <new>
+
+struct mt_encoder {
+  int dim, heads, hidden, depth;
+  float eps;
+  std::vector<mt_block_weights> blocks;
+};
+
+namespace {
+struct WsLayout {
+  size_t h, qkv, attn, mid, xo0, xo1, hid, total;
+};
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+WsLayout ws_layout(const mt_encoder* e, size_t M) {
+  WsLayout w;
+  size_t off = 0;
+  auto take = [&](size_t elems) { size_t o = off; off = align_up(off + elems * 2, 1024); return o; };
+  w.h = take(M * e->dim);
+  w.qkv = take(M * 3 * e->dim);
+  w.attn = take(M * e->dim);
+  w.mid = take(M * e->dim);
+  w.xo0 = take(M * e->dim);
+  w.xo1 = take(M * e->dim);
+  w.hid = take(M * e->hidden);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" int mt_encoder_create(mt_encoder** out, int dim, int heads, int hidden, int depth, float eps,
+                                 const mt_block_weights* blocks) {
+  using namespace mt;
+  MT_REQUIRE(out && blocks, MT_ERR_BAD_SHAPE, "mt_encoder_create: null pointer");
+  MT_REQUIRE(dim > 0 && heads > 0 && hidden > 0 && depth > 0, MT_ERR_BAD_SHAPE, "mt_encoder_create: bad sizes");
+  MT_REQUIRE(dim % heads == 0 && dim / heads == 64, MT_ERR_UNSUPPORTED,
+             "mt_encoder_create: head_dim must be 64 (dim=%d heads=%d)", dim, heads);
+  MT_REQUIRE(dim % 32 == 0 && hidden % 32 == 0, MT_ERR_BAD_SHAPE, "mt_encoder_create: dim/hidden must be multiples of 32");
+  for (int l = 0; l < depth; ++l) {
+    const mt_block_weights& b = blocks[l];
+    MT_REQUIRE(b.ln1_w && b.ln1_b && b.qkv_w && b.proj_w && b.ln2_w && b.ln2_b && b.fc1_w && b.fc2_w, MT_ERR_BAD_SHAPE,
+               "mt_encoder_create: block %d has a null weight pointer", l);
+  }
+  mt_encoder* e = new (std::nothrow) mt_encoder;
+  MT_REQUIRE(e, MT_ERR_CUDA, "mt_encoder_create: out of host memory");
+  e->dim = dim; e->heads = heads; e->hidden = hidden; e->depth = depth; e->eps = eps;
+  e->blocks.assign(blocks, blocks + depth);
+  *out = e;
+  return MT_OK;
+}
+
+extern "C" int mt_encoder_destroy(mt_encoder* enc) {
+  delete enc;
+  return MT_OK;
+}
+
+extern "C" int mt_encoder_workspace_bytes(const mt_encoder* enc, int B, int N, size_t* bytes) {
+  using namespace mt;
+  MT_REQUIRE(enc && bytes, MT_ERR_BAD_SHAPE, "mt_encoder_workspace_bytes: null pointer");
+  MT_REQUIRE(B > 0 && N > 0, MT_ERR_BAD_SHAPE, "mt_encoder_workspace_bytes: B and N must be positive");
+  *bytes = ws_layout(enc, size_t(B) * N).total;
+  return MT_OK;
+}
+
+extern "C" int mt_encoder_launches_per_forward(const mt_encoder* enc) { return enc ? 7 * enc->depth : 0; }
+
+extern "C" int mt_encoder_forward(mt_encoder* enc, const void* x, void* y, int B, int N, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(enc && x && y && workspace, MT_ERR_BAD_SHAPE, "mt_encoder_forward: null pointer");
+  MT_REQUIRE(B > 0 && N > 0, MT_ERR_BAD_SHAPE, "mt_encoder_forward: B and N must be positive");
+  MT_REQUIRE((long long)B * N < (1ll << 31) / 4096, MT_ERR_BAD_SHAPE, "mt_encoder_forward: B*N too large");
+  const int M = B * N;
+  const WsLayout w = ws_layout(enc, size_t(M));
+  MT_REQUIRE(workspace_bytes >= w.total, MT_ERR_BAD_SHAPE, "mt_encoder_forward: workspace too small (%zu < %zu)",
+             workspace_bytes, w.total);
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, MT_ERR_BAD_ALIGN,
+             "mt_encoder_forward: workspace must be 1024-byte aligned");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* h = ws + w.h;
+  void* qkv = ws + w.qkv;
+  void* attn = ws + w.attn;
+  void* mid = ws + w.mid;
+  void* xo[2] = {ws + w.xo0, ws + w.xo1};
+  void* hid = ws + w.hid;
+  const int d = enc->dim;
+  const float scale = 0.125f;  // head_dim^-0.5 with head_dim = 64
+  const void* cur = x;
+  for (int l = 0; l < enc->depth; ++l) {
+    const mt_block_weights& bw = enc->blocks[l];
+    void* outp = (l == enc->depth - 1) ? y : xo[l & 1];
+    int rc;
+    if ((rc = mt_layernorm(cur, MT_DT_BF16, bw.ln1_w, bw.ln1_b, h, M, d, enc->eps, stream))) return rc;
+    if ((rc = mt_gemm_bf16(h, bw.qkv_w, bw.qkv_b, nullptr, qkv, M, 3 * d, d, 0, 0, stream))) return rc;
+    if ((rc = mt_attention_fwd(qkv, attn, B, N, enc->heads, 64, scale, stream))) return rc;
+    if ((rc = mt_gemm_bf16(attn, bw.proj_w, bw.proj_b, cur, mid, M, d, d, 0, 0, stream))) return rc;
+    if ((rc = mt_layernorm(mid, MT_DT_BF16, bw.ln2_w, bw.ln2_b, h, M, d, enc->eps, stream))) return rc;
+    if ((rc = mt_gemm_bf16(h, bw.fc1_w, bw.fc1_b, nullptr, hid, M, enc->hidden, d, 1, 0, stream))) return rc;
+    if ((rc = mt_gemm_bf16(hid, bw.fc2_w, bw.fc2_b, mid, outp, M, d, enc->hidden, 0, 0, stream))) return rc;
+    cur = outp;
+  }
+  return MT_OK;
+}

@@ -1,0 +1,385 @@
+// mt_gemm.cu — bf16 "TN" GEMM with fused epilogue for the encoder's four Linear layers
+//   Y[M,N] = epi( X[M,K] · W[N,K]^T + bias[N] ) (+ R[M,N])
+// (E3 qkv, E5 proj+residual, E6 fc1+GELU / fc2+residual in SURVEY.md §8a; the reference runs these as
+//  F.linear + separate GELU / add kernels: PointCloud/openpoints/models/layers/attention.py:28,36,56-57,
+//  mlp.py:29-35.)
+//
+// Blackwell design (sm_100a only):
+//   * persistent CTAs (one per SM), static round-robin tile schedule, N-tile index fastest so the CTAs that
+//     run concurrently share the same activation rows and the whole weight matrix in L2;
+//   * operands staged by TMA (128B swizzle) into a kStages-deep smem ring with full/empty mbarriers;
+//   * tcgen05.mma (kind::f16, bf16 in / fp32 accumulate) issued by one thread, accumulators in TMEM,
+//     two accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * CG = 2: CTA pairs (cta_group::2): one 256x256 output tile per pair, each CTA loads its own 128 rows of X
+//     and half (128 rows) of the W tile, halving per-SM operand traffic from L2;
+//   * 8 epilogue warps: TMEM -> registers (tcgen05.ld) -> bias / exact-erf GELU / residual -> bf16 ->
+//     swizzled smem -> TMA store (coalesced, clips the M/N tails in hardware).
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warp 3 idle, warps 4..11 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half).
+#include "mt_ptx.cuh"
+#include "mt_common.cuh"
+
+namespace mt {
+
+constexpr int kBM = 128;         // rows of X per CTA
+constexpr int kBN = 256;         // UMMA N
+constexpr int kBK = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * kBN;  // 512
+constexpr int kEpiStageBytes = 32 * 128;     // per-warp staging: 32 rows x 64 bf16
+constexpr int kBiasBytes = 128 * 4;          // per-warp bias slice: 128 fp32
+
+template <int CG>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;                       // 16 KB
+  static constexpr int kBRows = (CG == 2) ? kBN / 2 : kBN;            // rows of W this CTA loads
+  static constexpr int kBBytes = kBRows * kBK * 2;                    // 16 / 32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (CG == 2) ? 5 : 3;
+  static constexpr int kSmemEpiOff = kStages * kStageBytes;
+  static constexpr int kSmemBiasOff = kSmemEpiOff + kEpiWarps * kEpiStageBytes;
+  static constexpr int kSmemBarOff = kSmemBiasOff + kEpiWarps * kBiasBytes;
+  static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
+  static constexpr int kSmemTmemPtrOff = kSmemBarOff + kNumBars * 8;
+  static constexpr int kSmemBytes = kSmemTmemPtrOff + 16 + 1024;  // +1024: manual 1 KB alignment slack
+};
+
+struct GemmParams {
+  const float* bias;            // [N] fp32 or nullptr
+  const __nv_bfloat16* resid;   // [M, ldr] bf16 or nullptr
+  int ldr;
+  int M, N, K;
+  int act;                      // 0 = identity, 1 = exact-erf GELU
+  int num_m_tiles, num_n_tiles;
+};
+
+// gelu(x) = x * Phi(x) with the exact (erf) definition, nn.GELU() default.
+// Evaluated as relu(x) - 0.5*|x|*erfc(|x|/sqrt2) with erfc(t/sqrt2) = 2^(t*p(t)); p = degree-4 minimax fit,
+// max abs error of the whole expression 5.6e-7 over all x (fit script: oracle/fit_gelu_poly.py).
+MT_DEVINL float gelu_erf(float x) {
+  const float t = fminf(fabsf(x), 12.0f);
+  float p = -0.00048811757005751133f;
+  p = fmaf(p, t, 0.007198806386440992f);
+  p = fmaf(p, t, -0.052146803587675095f);
+  p = fmaf(p, t, -0.4595957100391388f);
+  p = fmaf(p, t, -1.1510006189346313f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * t));
+  return fmaf(t * e, -0.5f, fmaxf(x, 0.0f));
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_y, const GemmParams p) {
+  using Cfg = GemmCfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  const int cluster_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_clusters = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+
+  const uint32_t bar_base = smem_base + Cfg::kSmemBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + kAccStages + s); };
+  const uint32_t tmem_ptr_addr = smem_base + Cfg::kSmemTmemPtrOff;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kSmemTmemPtrOff);
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_y);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), CG);   // leader: arrive.expect_tx, peer: remote arrive
+      mbar_init(empty_bar(s), 1);   // one tcgen05.commit per use
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(tfull_bar(s), 1);                 // tcgen05.commit
+      mbar_init(tempty_bar(s), CG * kEpiWarps);   // one arrive per epilogue warp (both CTAs)
+    }
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 2) tmem_alloc<CG>(tmem_ptr_addr, kTmemCols);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full_leader_base = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m_tile = t / p.num_n_tiles, n_tile = t % p.num_n_tiles;
+        const int row_a = m_tile * (kBM * CG) + int(rank) * kBM;
+        const int row_b = n_tile * kBN + ((CG == 2) ? int(rank) * (kBN / 2) : 0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          if constexpr (CG == 2) {
+            const uint32_t fb = full_leader_base + 8u * stage;
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg::kStageBytes);
+            else mbar_arrive_remote(full_bar(stage), 0);
+            tma_load_2d_cg2(sa, &tm_a, fb, kb * kBK, row_a, kEvictNormal);
+            tma_load_2d_cg2(sb, &tm_b, fb, kb * kBK, row_b, kEvictLast);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_2d(sa, &tm_a, full_bar(stage), kb * kBK, row_a, kEvictNormal);
+            tma_load_2d(sb, &tm_b, full_bar(stage), kb * kBK, row_b, kEvictLast);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM * CG, kBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * kBN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+            umma_f16_ss<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if constexpr (CG == 2) umma_commit_cg2_mc(empty_bar(stage), 0x3);
+          else umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        if constexpr (CG == 2) umma_commit_cg2_mc(tfull_bar(as), 0x3);
+        else umma_commit(tfull_bar(as));
+        if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===================================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int hf = (warp - 4) >> 2;  // column half of the 256-wide tile
+    const int ew = warp - 4;
+    const uint32_t stg = smem_base + Cfg::kSmemEpiOff + ew * kEpiStageBytes;
+    float* bias_s = reinterpret_cast<float*>(smem_gen + Cfg::kSmemBiasOff + ew * kBiasBytes);
+    int as = 0;
+    uint32_t aphase = 0;
+    bool store_pending = false;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m_tile = t / p.num_n_tiles, n_tile = t % p.num_n_tiles;
+      const int row0 = m_tile * (kBM * CG) + int(rank) * kBM + 32 * q;  // first row of this warp
+      const int col0 = n_tile * kBN + 128 * hf;                          // first column of this warp
+      const int row = row0 + lane;
+      // bias slice for this warp's 128 columns -> private smem (float4 per lane)
+      {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = col0 + 4 * lane;
+        if (p.bias != nullptr && c < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + c);
+        __syncwarp();
+        reinterpret_cast<float4*>(bias_s)[lane] = b4;
+        __syncwarp();
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(32 * q) << 16) + uint32_t(as * kBN + 128 * hf);
+#pragma unroll 1
+      for (int sc = 0; sc < 4; ++sc) {  // four 32-column slices; two slices = one 64-column TMA store
+        const int c_sc = col0 + 32 * sc;
+        // residual slice (64 B per row) — issued before the TMEM load so the latency overlaps
+        uint4 rv[4];
+        const bool has_res = (p.resid != nullptr) && (row < p.M) && (c_sc < p.N);
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + size_t(row) * p.ldr + c_sc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[j] = __ldg(rp + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(t_row + uint32_t(32 * sc), acc);
+        tmem_wait_ld();
+        if (sc == 3) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_remote(tempty_bar(as), 0);
+            else mbar_arrive(tempty_bar(as));
+          }
+        }
+        if ((sc & 1) == 0 && store_pending) {
+          // staging buffer is about to be overwritten: previous TMA store must have read it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          store_pending = false;
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = reinterpret_cast<const float4*>(bias_s)[8 * sc + j];
+          float v0 = __uint_as_float(acc[4 * j + 0]) + b4.x;
+          float v1 = __uint_as_float(acc[4 * j + 1]) + b4.y;
+          float v2 = __uint_as_float(acc[4 * j + 2]) + b4.z;
+          float v3 = __uint_as_float(acc[4 * j + 3]) + b4.w;
+          if (p.act == 1) {
+            v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+          }
+          const uint32_t r01 = (j & 1) ? rv[j >> 1].z : rv[j >> 1].x;  // columns 4j, 4j+1
+          const uint32_t r23 = (j & 1) ? rv[j >> 1].w : rv[j >> 1].y;  // columns 4j+2, 4j+3
+          v0 += bf16_lo(r01); v1 += bf16_hi(r01);
+          v2 += bf16_lo(r23); v3 += bf16_hi(r23);
+          packed[2 * j + 0] = pack_bf16x2(v0, v1);
+          packed[2 * j + 1] = pack_bf16x2(v2, v3);
+        }
+        // swizzled (128B pattern) store into the staging tile: row = lane, 16B chunk index ^ (row & 7)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = (sc & 1) * 4 + j;
+          const uint32_t addr = stg + uint32_t(lane * 128) + uint32_t(((chunk ^ (lane & 7)) << 4));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j + 0]),
+                       "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                       : "memory");
+        }
+        if (sc & 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && (c_sc - 32) < p.N) {
+            tma_store_2d(&tm_y, stg, c_sc - 32, row0);
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
+      }
+      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
+  }
+
+  // ---- teardown ----
+  __syncwarp();  // re-converge the single-lane role loops before the aligned barrier
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int CG>
+static int launch_gemm(const void* x, const void* w, const float* bias, const void* resid, int ldr, void* y, int M,
+                       int N, int K, int act, cudaStream_t stream) {
+  using Cfg = GemmCfg<CG>;
+  CUtensorMap tm_a, tm_b, tm_y;
+  {
+    uint64_t dims[2] = {uint64_t(K), uint64_t(M)};
+    uint64_t strides[1] = {uint64_t(K) * 2};
+    uint32_t box[2] = {uint32_t(kBK), uint32_t(kBM)};
+    int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
+    uint64_t strides[1] = {uint64_t(K) * 2};
+    uint32_t box[2] = {uint32_t(kBK), uint32_t(Cfg::kBRows)};
+    int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(N), uint64_t(M)};
+    uint64_t strides[1] = {uint64_t(N) * 2};
+    uint32_t box[2] = {64u, 32u};
+    int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.bias = bias;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(resid);
+  p.ldr = ldr;
+  p.M = M; p.N = N; p.K = K;
+  p.act = act;
+  p.num_m_tiles = ceil_div(M, kBM * CG);
+  p.num_n_tiles = ceil_div(N, kBN);
+
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int clusters = sms / CG;
+  if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters < 1) clusters = 1;
+
+  auto kern = gemm_bf16_kernel<CG>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(clusters * CG), 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CG;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  MT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, tm_y, p));
+  return MT_OK;
+}
+
+}  // namespace mt
+
+extern "C" int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int M,
+                            int N, int K, int act, int cta_group, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && w && y, MT_ERR_BAD_SHAPE, "mt_gemm_bf16: null pointer");
+  MT_REQUIRE(M > 0 && N > 0 && K > 0, MT_ERR_BAD_SHAPE, "mt_gemm_bf16: M,N,K must be positive (got %d,%d,%d)", M, N, K);
+  MT_REQUIRE(K % 8 == 0 && N % 8 == 0, MT_ERR_BAD_SHAPE,
+             "mt_gemm_bf16: K and N must be multiples of 8 (16-byte rows for TMA); got K=%d N=%d", K, N);
+  MT_REQUIRE(N % 32 == 0, MT_ERR_BAD_SHAPE, "mt_gemm_bf16: N must be a multiple of 32 (got %d)", N);
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_gemm_bf16: all pointers must be 16-byte aligned");
+  MT_REQUIRE(act == 0 || act == 1, MT_ERR_UNSUPPORTED, "mt_gemm_bf16: act must be 0 (none) or 1 (gelu)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cta_group == 1) return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, s);
+  if (cta_group == 2 || cta_group == 0) return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, s);
+  set_error("mt_gemm_bf16: cta_group must be 0 (auto), 1 or 2");
+  return MT_ERR_UNSUPPORTED;
+}

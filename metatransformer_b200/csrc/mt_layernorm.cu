@@ -1,0 +1,140 @@
+// mt_layernorm.cu — LayerNorm over the feature dim (E2 in SURVEY.md §8a): norm1 / norm2 of the timm Block
+// (PointCloud/openpoints/models/layers/attention.py:46,50,56-57; eps = 1e-5 because README.md:131 passes a bare
+// nn.LayerNorm).  Statistics in fp32 with the two-pass (mean, then centred second moment) formulation, biased
+// variance, exactly as F.layer_norm; output bf16 (it only ever feeds a bf16 tensor-core GEMM).
+//
+// HBM-bound: one warp owns one row, the row stays in registers between the passes, 16-byte loads/stores,
+// algorithmic traffic = M*d*(sizeof(in) + 2) bytes.
+#include "mt_ptx.cuh"
+#include "mt_common.cuh"
+
+namespace mt {
+
+constexpr int kLnWarps = 8;
+
+template <typename TIn>
+MT_DEVINL void load8(const TIn* p, float (&v)[8]);
+template <>
+MT_DEVINL void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+  v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+}
+template <>
+MT_DEVINL void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+MT_DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// NV > 0: d == NV*256 exactly, row held in registers.  NV == 0: any d % 8 == 0, row re-read (L1/L2 hits).
+template <int NV, typename TIn>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, int M, int d, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + warp;
+  if (row >= M) return;
+  const TIn* xr = x + size_t(row) * d;
+  __nv_bfloat16* yr = y + size_t(row) * d;
+  const float inv_d = 1.0f / float(d);
+
+  if constexpr (NV > 0) {
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      load8<TIn>(xr + (lane + 32 * i) * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float c = v[i][j] - mean; q = fmaf(c, c, q); }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c0 = (lane + 32 * i) * 8;
+      float g[8], b[8];
+      load8<float>(gamma + c0, g);
+      load8<float>(beta + c0, b);
+      uint4 o;
+      o.x = pack_bf16x2(fmaf((v[i][0] - mean) * rstd, g[0], b[0]), fmaf((v[i][1] - mean) * rstd, g[1], b[1]));
+      o.y = pack_bf16x2(fmaf((v[i][2] - mean) * rstd, g[2], b[2]), fmaf((v[i][3] - mean) * rstd, g[3], b[3]));
+      o.z = pack_bf16x2(fmaf((v[i][4] - mean) * rstd, g[4], b[4]), fmaf((v[i][5] - mean) * rstd, g[5], b[5]));
+      o.w = pack_bf16x2(fmaf((v[i][6] - mean) * rstd, g[6], b[6]), fmaf((v[i][7] - mean) * rstd, g[7], b[7]));
+      *reinterpret_cast<uint4*>(yr + c0) = o;
+    }
+  } else {
+    const int nchunks = d >> 3;
+    float s = 0.f;
+    for (int c = lane; c < nchunks; c += 32) {
+      float v[8];
+      load8<TIn>(xr + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+    for (int c = lane; c < nchunks; c += 32) {
+      float v[8];
+      load8<TIn>(xr + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float t = v[j] - mean; q = fmaf(t, t, q); }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    for (int c = lane; c < nchunks; c += 32) {
+      float v[8], g[8], b[8];
+      load8<TIn>(xr + c * 8, v);
+      load8<float>(gamma + c * 8, g);
+      load8<float>(beta + c * 8, b);
+      uint4 o;
+      o.x = pack_bf16x2(fmaf((v[0] - mean) * rstd, g[0], b[0]), fmaf((v[1] - mean) * rstd, g[1], b[1]));
+      o.y = pack_bf16x2(fmaf((v[2] - mean) * rstd, g[2], b[2]), fmaf((v[3] - mean) * rstd, g[3], b[3]));
+      o.z = pack_bf16x2(fmaf((v[4] - mean) * rstd, g[4], b[4]), fmaf((v[5] - mean) * rstd, g[5], b[5]));
+      o.w = pack_bf16x2(fmaf((v[6] - mean) * rstd, g[6], b[6]), fmaf((v[7] - mean) * rstd, g[7], b[7]));
+      *reinterpret_cast<uint4*>(yr + c * 8) = o;
+    }
+  }
+}
+
+template <typename TIn>
+static int launch_ln(const void* x, const float* gamma, const float* beta, void* y, int M, int d, float eps,
+                     cudaStream_t s) {
+  const TIn* xp = reinterpret_cast<const TIn*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  const unsigned grid = unsigned(ceil_div(M, kLnWarps));
+  const unsigned block = kLnWarps * 32;
+  if (d == 768) layernorm_kernel<3, TIn><<<grid, block, 0, s>>>(xp, gamma, beta, yp, M, d, eps);
+  else if (d == 1024) layernorm_kernel<4, TIn><<<grid, block, 0, s>>>(xp, gamma, beta, yp, M, d, eps);
+  else layernorm_kernel<0, TIn><<<grid, block, 0, s>>>(xp, gamma, beta, yp, M, d, eps);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+}  // namespace mt
+
+extern "C" int mt_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int M, int d,
+                            float eps, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && gamma && beta && y, MT_ERR_BAD_SHAPE, "mt_layernorm: null pointer");
+  MT_REQUIRE(M > 0 && d > 0 && d % 8 == 0, MT_ERR_BAD_SHAPE, "mt_layernorm: need M > 0 and d %% 8 == 0 (M=%d d=%d)", M,
+             d);
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
+               reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_layernorm: pointers must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (x_dtype == MT_DT_BF16) return launch_ln<__nv_bfloat16>(x, gamma, beta, y, M, d, eps, s);
+  if (x_dtype == MT_DT_F32) return launch_ln<float>(x, gamma, beta, y, M, d, eps, s);
+  set_error("mt_layernorm: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
+  return MT_ERR_BAD_DTYPE;
+}

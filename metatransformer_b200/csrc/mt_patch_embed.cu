@@ -1,0 +1,132 @@
+// mt_patch_embed.cu — the gather half of the Data2Seq conv tokenizers (T1/T2/T3 in SURVEY.md §8a).
+// A Conv2d/Conv3d whose kernel tiles the input (Data2Seq/Image.py:16 Conv2d(3,d,16,16);
+// Video/models/modeling_finetune.py:285-289 Conv3d(3,d,(2,16,16),(2,16,16)); Audio/src/models/ast_models.py:86
+// Conv2d(1,d,(16,16),stride=(fstride,tstride))) is a GEMM over im2row patches:
+//   tokens[m, :] = rows[m, :] @ weight.view(d, -1)^T + bias,  m = ((b*Tp + tp)*Hp + hp)*Wp + wp,
+//   rows[m, ((c*kt + dt)*kh + dh)*kw + dw] = x[b, c, tp*st + dt, hp*sh + dh, wp*sw + dw]
+// which also yields the (B, N, d) token layout of `.flatten(2).transpose(1, 2)` (Image.py:26) directly.
+// This kernel builds `rows` in bf16 (cast fused into the gather); the GEMM + bias runs in mt_gemm_bf16.
+//
+// HBM-bound: algorithmic bytes = B*C*T*H*W*sizeof(in) (read once when stride == kernel) + M*K*2 (write).
+// Mapping: one thread per 8 consecutive dw (16-byte bf16 store; 2x16-byte fp32 loads), consecutive threads
+// walk K fastest so stores are fully coalesced and loads are whole 32/64-byte segments.
+#include "mt_ptx.cuh"
+#include "mt_common.cuh"
+
+namespace mt {
+
+struct Im2RowParams {
+  int B, C, T, H, W;
+  int kt, kh, kw, st, sh, sw;
+  int Tp, Hp, Wp;
+  int K;            // C*kt*kh*kw
+  long long M;      // B*Tp*Hp*Wp
+};
+
+template <typename TIn>
+MT_DEVINL float ld_as_f32(const TIn* p);
+template <> MT_DEVINL float ld_as_f32<float>(const float* p) { return __ldg(p); }
+template <> MT_DEVINL float ld_as_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+// VEC = true: kw % 8 == 0 and every 8-pixel segment is 16-byte (bf16) / 32-byte (fp32) aligned.
+template <typename TIn, bool VEC>
+__global__ void __launch_bounds__(256)
+im2row_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const Im2RowParams p) {
+  const int k8_per_row = p.K >> 3;
+  const long long total = p.M * k8_per_row;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long m = idx / k8_per_row;
+    const int k0 = int(idx - m * k8_per_row) << 3;
+    // token coordinates
+    long long r = m;
+    const int wp = int(r % p.Wp); r /= p.Wp;
+    const int hp = int(r % p.Hp); r /= p.Hp;
+    const int tp = int(r % p.Tp);
+    const int b = int(r / p.Tp);
+    uint4 o;
+    if constexpr (VEC) {
+      // k0 -> (c, dt, dh, dw0), dw0 multiple of 8
+      int kk = k0;
+      const int dw0 = kk % p.kw; kk /= p.kw;
+      const int dh = kk % p.kh; kk /= p.kh;
+      const int dt = kk % p.kt;
+      const int c = kk / p.kt;
+      const size_t off = (((size_t(b) * p.C + c) * p.T + (tp * p.st + dt)) * p.H + (hp * p.sh + dh)) * size_t(p.W) +
+                         size_t(wp * p.sw + dw0);
+      if constexpr (sizeof(TIn) == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + off));
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(x + off) + 1);
+        o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(c4.x, c4.y); o.w = pack_bf16x2(c4.z, c4.w);
+      } else {
+        o = __ldg(reinterpret_cast<const uint4*>(x + off));
+      }
+    } else {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int kk = k0 + j;
+        const int dw = kk % p.kw; kk /= p.kw;
+        const int dh = kk % p.kh; kk /= p.kh;
+        const int dt = kk % p.kt;
+        const int c = kk / p.kt;
+        const size_t off = (((size_t(b) * p.C + c) * p.T + (tp * p.st + dt)) * p.H + (hp * p.sh + dh)) * size_t(p.W) +
+                           size_t(wp * p.sw + dw);
+        v[j] = ld_as_f32<TIn>(x + off);
+      }
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    }
+    *reinterpret_cast<uint4*>(rows + size_t(m) * p.K + k0) = o;
+  }
+}
+
+template <typename TIn>
+static int launch_im2row(const void* x, void* rows, const Im2RowParams& p, cudaStream_t s) {
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const long long total = p.M * (p.K >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sms * 32) blocks = (long long)sms * 32;
+  if (blocks < 1) blocks = 1;
+  const int elt = int(sizeof(TIn));
+  const int seg_align = 16 / elt * ((elt == 4) ? 1 : 1);  // elements per 16 bytes
+  // vector path needs each 8-pixel segment start (wp*sw + dw0, row stride W) to sit on a 16-byte boundary
+  const bool vec = (p.kw % 8 == 0) && (p.W % seg_align == 0) && (p.sw % seg_align == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (8 % seg_align == 0);
+  const TIn* xp = reinterpret_cast<const TIn*>(x);
+  __nv_bfloat16* rp = reinterpret_cast<__nv_bfloat16*>(rows);
+  if (vec) im2row_kernel<TIn, true><<<unsigned(blocks), 256, 0, s>>>(xp, rp, p);
+  else im2row_kernel<TIn, false><<<unsigned(blocks), 256, 0, s>>>(xp, rp, p);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+}  // namespace mt
+
+extern "C" int mt_im2row(const void* x, int x_dtype, void* rows, int B, int C, int T, int H, int W, int kt, int kh,
+                         int kw, int st, int sh, int sw, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && rows, MT_ERR_BAD_SHAPE, "mt_im2row: null pointer");
+  MT_REQUIRE(B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && kt > 0 && kh > 0 && kw > 0 && st > 0 && sh > 0 && sw > 0,
+             MT_ERR_BAD_SHAPE, "mt_im2row: all sizes must be positive");
+  MT_REQUIRE(T >= kt && H >= kh && W >= kw, MT_ERR_BAD_SHAPE, "mt_im2row: kernel (%d,%d,%d) larger than input (%d,%d,%d)",
+             kt, kh, kw, T, H, W);
+  Im2RowParams p;
+  p.B = B; p.C = C; p.T = T; p.H = H; p.W = W;
+  p.kt = kt; p.kh = kh; p.kw = kw; p.st = st; p.sh = sh; p.sw = sw;
+  p.Tp = (T - kt) / st + 1; p.Hp = (H - kh) / sh + 1; p.Wp = (W - kw) / sw + 1;
+  p.K = C * kt * kh * kw;
+  p.M = (long long)B * p.Tp * p.Hp * p.Wp;
+  MT_REQUIRE(p.K % 8 == 0, MT_ERR_BAD_SHAPE, "mt_im2row: C*kt*kh*kw must be a multiple of 8 (got %d)", p.K);
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(rows) & 15) == 0, MT_ERR_BAD_ALIGN, "mt_im2row: rows must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (x_dtype == MT_DT_F32) return launch_im2row<float>(x, rows, p, s);
+  if (x_dtype == MT_DT_BF16) return launch_im2row<__nv_bfloat16>(x, rows, p, s);
+  set_error("mt_im2row: x_dtype must be fp32 or bf16 (got %d)", x_dtype);
+  return MT_ERR_BAD_DTYPE;
+}

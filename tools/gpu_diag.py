@@ -1,0 +1,219 @@
+"""GPU bring-up diagnostics: each group runs in its own subprocess (a trapped kernel cannot poison the rest).
+
+    python tools/gpu_diag.py            # run every group, logs under gpurun_out/diag/
+    python tools/gpu_diag.py gemm1      # run one group in-process
+
+Not a test-suite (tests/ holds the parity tests); this prints error *patterns* to debug descriptor/layout bugs.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def _report(name, got, ref, tol=2e-2):
+    import torch
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    rel = err.max().item() / denom
+    bad = err > tol * max(denom, 1e-6)
+    nb = int(bad.sum())
+    nan = int(torch.isnan(got).sum())
+    status = "OK " if (nb == 0 and nan == 0) else "BAD"
+    print(f"[{status}] {name}: max_abs_err={err.max().item():.4g} rel_to_max={rel:.3g} ref_max={denom:.4g} "
+          f"bad={nb}/{bad.numel()} nan={nan}", flush=True)
+    if nb and got.dim() == 2:
+        rows = bad.any(dim=1).nonzero().flatten()
+        cols = bad.any(dim=0).nonzero().flatten()
+        print(f"      bad rows: n={rows.numel()} first={rows[:12].tolist()} last={rows[-4:].tolist()}")
+        print(f"      bad cols: n={cols.numel()} first={cols[:12].tolist()} last={cols[-4:].tolist()}")
+        r, c = int(rows[0]), int(cols[0])
+        print(f"      got[{r},{c}:{c+8}]={got[r, c:c+8].tolist()}")
+        print(f"      ref[{r},{c}:{c+8}]={ref[r, c:c+8].tolist()}")
+    return nb == 0 and nan == 0
+
+
+def group_basic():
+    import torch
+    from metatransformer_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(1000, 768, device=dev)
+    y = ops.cast(x, torch.bfloat16)
+    _report("cast f32->bf16", y, x.bfloat16())
+    for (M, d, dt) in [(777, 768, torch.bfloat16), (513, 1024, torch.float32), (100, 200, torch.bfloat16),
+                       (64, 4096, torch.float32)]:
+        x = (torch.randn(M, d, device=dev) * 2 + 0.5).to(dt)
+        g = torch.randn(d, device=dev) * 0.1 + 1
+        b = torch.randn(d, device=dev) * 0.1
+        y = ops.layernorm(x, g, b, 1e-5)
+        ref = torch.nn.functional.layer_norm(x.float(), (d,), g, b, 1e-5)
+        _report(f"layernorm M={M} d={d} {dt}", y, ref, tol=1e-2)
+    # im2row
+    for (shape, k, s) in [((2, 3, 1, 224, 224), (1, 16, 16), (1, 16, 16)), ((2, 3, 4, 32, 32), (2, 16, 16), (2, 16, 16)),
+                          ((2, 1, 1, 128, 100), (1, 16, 16), (1, 10, 10))]:
+        x = torch.randn(*shape, device=dev)
+        rows, (Tp, Hp, Wp) = ops.im2row(x, k, s)
+        B, C = shape[0], shape[1]
+        pat = x.unfold(2, k[0], s[0]).unfold(3, k[1], s[1]).unfold(4, k[2], s[2])  # B,C,Tp,Hp,Wp,kt,kh,kw
+        ref = pat.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(B * Tp * Hp * Wp, -1)
+        _report(f"im2row {shape} k={k} s={s}", rows, ref.bfloat16())
+    torch.cuda.synchronize()
+
+
+def _gemm_case(cg, M, N, K, bias, gelu, resid, ints=False, seed=0):
+    import torch
+    from metatransformer_b200 import ops
+    torch.manual_seed(seed)
+    dev = "cuda"
+    if ints:
+        x = torch.randint(-2, 3, (M, K), device=dev).bfloat16()
+        w = torch.randint(-2, 3, (N, K), device=dev).bfloat16()
+    else:
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    b = (torch.randn(N, device=dev) * 0.5) if bias else None
+    r = torch.randn(M, N, device=dev).bfloat16() if resid else None
+    y = ops.linear(x, w, b, r, gelu=gelu, cta_group=cg)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    if resid:
+        ref = ref + r.float()
+    return _report(f"gemm cg={cg} M={M} N={N} K={K} bias={bias} gelu={gelu} resid={resid} ints={ints}", y, ref,
+                   tol=1e-2)
+
+
+def _group_gemm(cg):
+    ok = True
+    ok &= _gemm_case(cg, 128 * cg, 256, 64, False, False, False, ints=True)
+    ok &= _gemm_case(cg, 128 * cg, 256, 128, False, False, False, ints=True)
+    ok &= _gemm_case(cg, 128 * cg, 256, 768, False, False, False)
+    ok &= _gemm_case(cg, 256 * cg, 512, 256, True, False, False)
+    ok &= _gemm_case(cg, 300, 768, 768, True, False, True)
+    ok &= _gemm_case(cg, 1568, 2304, 768, True, False, False)
+    ok &= _gemm_case(cg, 1568, 3072, 768, True, True, False)
+    ok &= _gemm_case(cg, 1568, 768, 3072, True, False, True)
+    ok &= _gemm_case(cg, 50176, 768, 768, True, False, True)
+    ok &= _gemm_case(cg, 1000, 320, 200, True, True, True)
+    return ok
+
+
+def group_gemm1():
+    _group_gemm(1)
+
+
+def group_gemm2():
+    _group_gemm(2)
+
+
+def _attn_case(B, N, H, seed=0):
+    import torch
+    from metatransformer_b200 import ops
+    torch.manual_seed(seed)
+    dev = "cuda"
+    qkv = torch.randn(B, N, 3 * H * 64, device=dev).bfloat16()
+    out = ops.attention(qkv, H)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    att = (q @ k.transpose(-2, -1)) * 0.125
+    ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(B, N, H * 64)
+    return _report(f"attention B={B} N={N} H={H}", out.reshape(B * N, -1), ref.reshape(B * N, -1), tol=1e-2)
+
+
+def group_attn():
+    _attn_case(1, 128, 1)
+    _attn_case(1, 64, 2)
+    _attn_case(2, 196, 3)
+    _attn_case(2, 256, 2)
+    _attn_case(1, 300, 2)
+    _attn_case(1, 512, 12)
+    _attn_case(2, 1568, 4)
+    _attn_case(64, 196, 12)
+
+
+def group_perf():
+    import torch
+    from metatransformer_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(0)
+
+    def timeit(fn, iters=20, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    M = 50176
+    for (N, K, gelu, resid, name) in [(2304, 768, False, False, "qkv"), (768, 768, False, True, "proj"),
+                                      (3072, 768, True, False, "fc1"), (768, 3072, False, True, "fc2")]:
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+        b = torch.randn(N, device=dev)
+        r = torch.randn(M, N, device=dev).bfloat16() if resid else None
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        for cg in (1, 2):
+            ms = timeit(lambda: ops.linear(x, w, b, r, gelu=gelu, cta_group=cg, out=out))
+            print(f"[perf] gemm {name} cg={cg} M={M} N={N} K={K}: {ms:.4f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s",
+                  flush=True)
+        ms = timeit(lambda: torch.nn.functional.linear(x, w))
+        print(f"[perf] cublas {name}: {ms:.4f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for (B, N, H) in [(256, 196, 12), (128, 256, 16), (64, 512, 12), (32, 1568, 16)]:
+        qkv = torch.randn(B, N, 3 * H * 64, device=dev).bfloat16()
+        out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.attention(qkv, H, out=out))
+        fl = 4.0 * B * H * N * N * 64
+        print(f"[perf] attention B={B} N={N} H={H}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    x = torch.randn(M, 768, device=dev).bfloat16()
+    g = torch.ones(768, device=dev)
+    bb = torch.zeros(768, device=dev)
+    out = torch.empty_like(x)
+    ms = timeit(lambda: ops.layernorm(x, g, bb, out=out))
+    print(f"[perf] layernorm M={M} d=768: {ms:.4f} ms  {M * 768 * 4 / ms / 1e6:.1f} GB/s", flush=True)
+
+
+GROUPS = {"basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+
+
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] in GROUPS:
+        GROUPS[sys.argv[1]]()
+        return
+    names = sys.argv[1:] if len(sys.argv) > 1 else list(GROUPS)
+    outdir = ROOT / "gpurun_out" / "diag"
+    outdir.mkdir(parents=True, exist_ok=True)
+    for name in names:
+        t0 = time.time()
+        log = outdir / f"{name}.log"
+        with open(log, "w") as f:
+            try:
+                r = subprocess.run([sys.executable, __file__, name], stdout=f, stderr=subprocess.STDOUT, timeout=300,
+                                   cwd=str(ROOT))
+                rc = r.returncode
+            except subprocess.TimeoutExpired:
+                rc = "TIMEOUT"
+        txt = log.read_text()
+        print(f"===== group {name}: rc={rc} ({time.time() - t0:.1f}s) =====")
+        print(txt[-6000:])
+        sys.stdout.flush()
+
+
+if __name__ == "__main__":
+    main()
