@@ -1,0 +1,138 @@
+"""Generate golden vectors by running the REFERENCE's own code (build container only: needs /root/reference).
+
+    python tests/golden/make_golden.py
+
+What is executed from the reference tree (never copied into this repo):
+  * PointCloud/openpoints/models/layers/attention.py  -> classes Attention, Block   ("borrowed from TIMM", :2)
+  * PointCloud/openpoints/models/layers/mlp.py        -> class Mlp
+    Their package-relative imports (`from . import create_norm, create_act, DropPath, ...`, `from .helpers import
+    to_2tuple`) pull in openpoints' registry machinery, which needs the absent `multimethod` package; we satisfy
+    exactly those names with tiny stand-ins (nn.LayerNorm(eps=1e-5) — the README path, README.md:131 — and nn.GELU())
+    and exec the two source files unmodified.
+  * Data2Seq/Image.py       -> PatchEmbed (imports only torch)
+  * Data2Seq/Time_Series.py -> DataEmbedding (imports only torch)
+The vectors land in tests/golden/*.npz (small, committed).  /root/reference does not exist on the GPU box, so tests
+only ever read the .npz files.
+"""
+from __future__ import annotations
+
+import importlib.util
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+
+def _load_reference_block_classes():
+    layers = REF / "PointCloud/openpoints/models/layers"
+    pkg = types.ModuleType("refpkg")
+    pkg.__path__ = [str(layers)]
+
+    def create_norm(norm_args, channels, dimension=None):
+        return nn.LayerNorm(channels)  # README.md:131 passes a bare nn.LayerNorm -> eps 1e-5
+
+    def create_act(act_args):
+        return nn.GELU()               # README.md:132 act_layer=nn.GELU
+
+    class DropPath(nn.Identity):       # only constructed when drop_path > 0 (attention.py:49); never here
+        def __init__(self, p=0.0):
+            super().__init__()
+
+    pkg.create_norm = create_norm
+    pkg.create_act = create_act
+    pkg.DropPath = DropPath
+    pkg.trunc_normal_ = nn.init.trunc_normal_
+    pkg.lecun_normal_ = lambda t: t
+    sys.modules["refpkg"] = pkg
+    helpers = types.ModuleType("refpkg.helpers")
+    helpers.to_2tuple = lambda x: x if isinstance(x, tuple) else (x, x)
+    sys.modules["refpkg.helpers"] = helpers
+
+    def load(name, fname):
+        spec = importlib.util.spec_from_file_location(f"refpkg.{name}", layers / fname)
+        mod = importlib.util.module_from_spec(spec)
+        mod.__package__ = "refpkg"
+        sys.modules[f"refpkg.{name}"] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    mlp_mod = load("mlp", "mlp.py")
+    pkg.Mlp = mlp_mod.Mlp
+    att_mod = load("attention", "attention.py")
+    return att_mod.Attention, att_mod.Block, mlp_mod.Mlp
+
+
+def _load_file_module(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _randomise(module: nn.Module, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            elif "norm" in name and name.endswith("weight"):
+                p.copy_(1.0 + torch.randn(p.shape, generator=g) * 0.1)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    Attention, Block, Mlp = _load_reference_block_classes()
+
+    # ---- encoder: nn.Sequential of the reference's Block, two configs (head_dim 64 like Base/Large, and 32) ----
+    for tag, (dim, heads, depth, B, N) in {"enc_d128_h2_L2": (128, 2, 2, 2, 37), "enc_d96_h3_L2": (96, 3, 2, 3, 50)}.items():
+        enc = nn.Sequential(*[Block(dim=dim, num_heads=heads, mlp_ratio=4., qkv_bias=True) for _ in range(depth)]).eval()
+        _randomise(enc, seed=len(tag) + dim)
+        g = torch.Generator().manual_seed(7)
+        x = torch.randn(B, N, dim, generator=g)
+        y = enc(x)
+        # per-stage intermediates of block 0 for finer-grained checks
+        b0 = enc[0]
+        h1 = b0.norm1(x)
+        a1 = b0.attn(h1)
+        x1 = x + a1
+        m1 = b0.mlp(b0.norm2(x1))
+        arrays = {"x": x.numpy(), "y": y.numpy(), "b0_norm1": h1.numpy(), "b0_attn": a1.numpy(), "b0_mlp": m1.numpy(),
+                  "meta": np.array([dim, heads, depth, B, N])}
+        for k, v in enc.state_dict().items():
+            arrays["sd." + k] = v.numpy()
+        np.savez_compressed(OUT / f"{tag}.npz", **arrays)
+        print(tag, "y abs max", float(y.abs().max()))
+
+    # ---- Data2Seq/Image.py PatchEmbed (the 'image' / 'infrared' / 'x-ray' tokenizer) ----
+    image_mod = _load_file_module("ref_image", REF / "Data2Seq/Image.py")
+    pe = image_mod.PatchEmbed(embed_dim=64).eval()
+    _randomise(pe, seed=3)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randint(-8, 9, (2, 3, 224, 224), generator=g).float() / 8.0   # exactly representable, compresses well
+    y = pe(x)
+    np.savez_compressed(OUT / "image_patch_embed.npz", x=x.numpy().astype(np.float16), y=y.numpy(),
+                        w=pe.proj.weight.numpy(), b=pe.proj.bias.numpy())
+    print("image_patch_embed", tuple(y.shape))
+
+    # ---- Data2Seq/Time_Series.py DataEmbedding (works with c_in=; eval => dropout identity) ----
+    ts_mod = _load_file_module("ref_ts", REF / "Data2Seq/Time_Series.py")
+    de = ts_mod.DataEmbedding(c_in=7, d_model=64).eval()
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(3, 96, 7, generator=g)
+    y = de(x)
+    np.savez_compressed(OUT / "time_series_embed.npz", x=x.numpy(), y=y.numpy(),
+                        w=de.value_embedding.tokenConv.weight.numpy())
+    print("time_series_embed", tuple(y.shape))
+
+
+if __name__ == "__main__":
+    main()
