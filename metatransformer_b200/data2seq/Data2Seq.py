@@ -1,0 +1,43 @@
+"""Data2Seq dispatcher drop-in (Data2Seq/Data2Seq.py:19-55): `Data2Seq(modality, dim)(data) -> (B, N, dim)`.
+
+Deviations from the file as shipped (it cannot be imported without `clip`, and several branches crash —
+SURVEY.md §8a row T0); the constructor / forward signature and attribute names (`modality`, `embed_dim`, `embed`)
+are kept and the *intended* semantics implemented:
+  image / infrared / x-ray : Image.PatchEmbed(embed_dim=dim)                              (Data2Seq.py:25-26)
+  video                    : Video.PatchEmbed(embed_dim=dim), VideoMAE tubelets           (Data2Seq.py:29-30)
+  audio                    : the reference has no `embed` for audio and returns a raw fbank (Data2Seq.py:38-45,53-54);
+                             here a (B, T, F) fbank is tokenised like AST (ast_models.py:86,152-155) with
+                             Acoustic.PatchEmbed(embed_dim=dim, fstride=10, tstride=10)
+  time-series / imu, text, graph, hyper : not built yet -> NotImplementedError
+"""
+import torch.nn as nn
+
+from . import Acoustic, Image, Video
+
+_IMAGE_LIKE = ('image', 'infrared', 'x-ray')
+_NEXT = ('text', 'graph', 'hyper', 'time-series', 'imu')
+
+
+class Data2Seq(nn.Module):
+
+    def __init__(self, modality, dim, token_dtype=None):
+        super().__init__()
+        self.modality = modality
+        self.embed_dim = dim
+        if self.modality in _IMAGE_LIKE:
+            self.embed = Image.PatchEmbed(embed_dim=self.embed_dim, token_dtype=token_dtype)
+        elif self.modality == 'video':
+            self.embed = Video.PatchEmbed(embed_dim=self.embed_dim, token_dtype=token_dtype)
+        elif self.modality == 'audio':
+            self.embed = Acoustic.PatchEmbed(embed_dim=self.embed_dim, fstride=10, tstride=10, token_dtype=token_dtype)
+        elif self.modality in _NEXT:
+            raise NotImplementedError(f"Data2Seq modality '{modality}' is not built on the B200 path yet "
+                                      "(SURVEY.md §8f rank 3)")
+        else:
+            raise ValueError(f"unknown modality '{modality}'")
+
+    def forward(self, data):
+        if self.modality == 'audio':
+            # (B, T, F) fbank -> (B, 1, F, T)   (Audio/src/models/ast_models.py:152-153)
+            data = data.unsqueeze(1).transpose(2, 3)
+        return self.embed(data)

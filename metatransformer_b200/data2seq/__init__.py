@@ -1,0 +1,5 @@
+"""Drop-in for the reference's `Data2Seq/` package (tokenizers feeding the shared encoder)."""
+from . import Acoustic, Image, Video
+from .Data2Seq import Data2Seq
+
+__all__ = ["Data2Seq", "Image", "Video", "Acoustic"]

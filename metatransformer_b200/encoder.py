@@ -1,0 +1,135 @@
+"""Whole-encoder fast path: one C call (`mt_encoder_forward`) for nn.Sequential(*[Block]*L).
+
+`build_encoder("base" | "large")` returns exactly the module the reference README builds (README.md:125-147), made of
+this package's drop-in Blocks; `FusedEncoder(seq)` wraps such a Sequential, packs its weights to bf16 once and runs
+all L blocks back to back on the current stream with a cached workspace (no per-op Python, no torch allocations).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import BlockWeights, check
+from .vision_transformer import Block, _packed, _layernorm_eps
+
+ENCODER_CONFIGS = {
+    # README.md:125-134 / :138-147
+    "base": dict(dim=768, num_heads=12, depth=12),
+    "large": dict(dim=1024, num_heads=16, depth=24),
+}
+
+
+def build_encoder(scale: str = "base", **overrides) -> nn.Sequential:
+    cfg = dict(ENCODER_CONFIGS[scale])
+    cfg.update(overrides)
+    depth = cfg.pop("depth")
+    return nn.Sequential(*[
+        Block(dim=cfg["dim"], num_heads=cfg["num_heads"], mlp_ratio=4., qkv_bias=True, norm_layer=nn.LayerNorm,
+              act_layer=nn.GELU) for _ in range(depth)])
+
+
+class FusedEncoder(nn.Module):
+    """Runs a Sequential of `Block`s through the C-ABI whole-encoder driver (inference / frozen-encoder forward)."""
+
+    def __init__(self, blocks: nn.Sequential):
+        super().__init__()
+        if len(blocks) == 0 or not all(isinstance(b, Block) for b in blocks):
+            raise TypeError("FusedEncoder needs a non-empty nn.Sequential of metatransformer_b200 Blocks")
+        self.blocks = blocks
+        self._handle = None
+        self._handle_key = None
+        self._keepalive = None
+        self._ws = None
+
+    # -- handle management --------------------------------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p in self.blocks.parameters())
+
+    def _ensure_handle(self):
+        key = self._weights_key()
+        if self._handle is not None and key == self._handle_key:
+            return
+        self._destroy()
+        lib = _lib.load()
+        b0 = self.blocks[0]
+        dim = b0.norm1.normalized_shape[0]
+        heads = b0.attn.num_heads
+        hidden = b0.mlp.fc1.out_features
+        eps = _layernorm_eps(b0.norm1)
+        arr = (BlockWeights * len(self.blocks))()
+        keep = []
+        for i, blk in enumerate(self.blocks):
+            if blk.attn.num_heads != heads or blk.mlp.fc1.out_features != hidden or _layernorm_eps(blk.norm1) != eps \
+                    or _layernorm_eps(blk.norm2) != eps or abs(blk.attn.scale - (dim // heads) ** -0.5) > 1e-12:
+                raise NotImplementedError("FusedEncoder: all blocks must share one configuration and the default scale")
+
+            def P(mod, name, param, dt):
+                t = _packed(mod, name, param, dt)
+                keep.append(t)
+                return None if t is None else t.data_ptr()
+
+            w = arr[i]
+            w.ln1_w = P(blk, "norm1.weight", blk.norm1.weight, torch.float32)
+            w.ln1_b = P(blk, "norm1.bias", blk.norm1.bias, torch.float32)
+            w.qkv_w = P(blk.attn, "qkv.weight", blk.attn.qkv.weight, torch.bfloat16)
+            w.qkv_b = P(blk.attn, "qkv.bias", blk.attn.qkv.bias, torch.float32)
+            w.proj_w = P(blk.attn, "proj.weight", blk.attn.proj.weight, torch.bfloat16)
+            w.proj_b = P(blk.attn, "proj.bias", blk.attn.proj.bias, torch.float32)
+            w.ln2_w = P(blk, "norm2.weight", blk.norm2.weight, torch.float32)
+            w.ln2_b = P(blk, "norm2.bias", blk.norm2.bias, torch.float32)
+            w.fc1_w = P(blk.mlp, "fc1.weight", blk.mlp.fc1.weight, torch.bfloat16)
+            w.fc1_b = P(blk.mlp, "fc1.bias", blk.mlp.fc1.bias, torch.float32)
+            w.fc2_w = P(blk.mlp, "fc2.weight", blk.mlp.fc2.weight, torch.bfloat16)
+            w.fc2_b = P(blk.mlp, "fc2.bias", blk.mlp.fc2.bias, torch.float32)
+        h = ctypes.c_void_p()
+        check(lib.mt_encoder_create(ctypes.byref(h), dim, heads, hidden, len(self.blocks), float(eps), arr),
+              "mt_encoder_create")
+        self._handle, self._handle_key, self._keepalive = h, key, keep
+        self.dim = dim
+
+    def _destroy(self):
+        if self._handle is not None:
+            _lib.load().mt_encoder_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    @property
+    def launches_per_forward(self) -> int:
+        self._ensure_handle()
+        return _lib.load().mt_encoder_launches_per_forward(self._handle)
+
+    # -- forward --------------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("FusedEncoder: CUDA (B200) tensors only; there is no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.blocks.parameters())):
+            raise NotImplementedError("FusedEncoder is forward-only; wrap the call in torch.no_grad()")
+        if self.training and any(m.p > 0 for m in self.blocks.modules() if isinstance(m, nn.Dropout)):
+            raise NotImplementedError("FusedEncoder: dropout in training mode is not supported")
+        self._ensure_handle()
+        lib = _lib.load()
+        B, N, C = x.shape
+        if C != self.dim:
+            raise ValueError(f"FusedEncoder: expected last dim {self.dim}, got {C}")
+        xin = x.contiguous()
+        xb = xin if xin.dtype == torch.bfloat16 else ops.cast(xin, torch.bfloat16)
+        y = out if (out is not None and out.dtype == torch.bfloat16) else torch.empty_like(xb)
+        need = ctypes.c_size_t()
+        check(lib.mt_encoder_workspace_bytes(self._handle, B, N, ctypes.byref(need)), "mt_encoder_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != x.device:
+            self._ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.mt_encoder_forward(self._handle, xb.data_ptr(), y.data_ptr(), B, N, self._ws.data_ptr(),
+                                         self._ws.numel(), torch.cuda.current_stream().cuda_stream), "mt_encoder_forward")
+        if x.dtype == torch.bfloat16:
+            return y
+        return ops.cast(y, x.dtype)

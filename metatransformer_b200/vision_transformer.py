@@ -1,0 +1,197 @@
+"""timm-compatible `Mlp`, `Attention`, `Block` whose forward runs on hand-written sm_100a kernels (libmt_b200.so).
+
+Drop-in for `from timm.models.vision_transformer import Block` as the reference uses it (README.md:116-149 and the
+eleven call sites listed in SURVEY.md §2.1 row 2): same constructor signature as timm 0.4.12 (plus timm 0.8's
+`init_values=None` for Tabular/README.md:31), same attribute / parameter names, hence the same state-dict keys
+("{i}.norm1.weight", "{i}.attn.qkv.weight", ...) so `encoder.load_state_dict(ckpt, strict=True)`
+works on the published checkpoints.  Reference math: PointCloud/openpoints/models/layers/attention.py:12-58,
+mlp.py:11-35 (verbatim timm copies).
+
+Precision model (documented in DESIGN.md): GEMM / attention operands bf16, fp32 accumulation, fp32 LayerNorm and
+softmax statistics, bf16 residual stream.  fp32 / fp16 inputs are converted at the module boundary and the result
+is returned in the input dtype.  There is NO CPU or eager fallback: CPU tensors, non-B200 devices or a missing
+extension raise.
+"""
+from __future__ import annotations
+
+from functools import partial
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+__all__ = ["Mlp", "Attention", "Block", "DropPath"]
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (timm.models.layers.DropPath).  Identity in eval mode / at rate 0."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        raise NotImplementedError("DropPath with rate > 0 in training mode is not implemented on the B200 path yet "
+                                  "(SURVEY.md §8f rank 2)")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parameter packing: bf16 matrices / fp32 vectors derived from the nn.Parameters, rebuilt lazily whenever the
+# parameter storage, version or device changes (nn.DataParallel replicas, .to(), load_state_dict, optimizer steps)
+# ------------------------------------------------------------------------------------------------------------------
+def _packed(module: nn.Module, name: str, param: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:
+    if param is None:
+        return None
+    cache = module.__dict__.setdefault("_mt_pack_cache", {})
+    key = (param.data_ptr(), param._version, param.device, param.dtype)
+    hit = cache.get(name)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    src = param.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    packed = src if src.dtype == dtype else ops.cast(src, dtype)
+    cache[name] = (key, packed)
+    return packed
+
+
+def _check_input(x: torch.Tensor, what: str) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(f"{what}: input is on {x.device}; metatransformer_b200 runs on B200 GPUs only and has no CPU "
+                           "fallback (use oracle/ for CPU reference numbers)")
+    if x.dim() != 3:
+        raise ValueError(f"{what}: expected (B, N, C) input, got shape {tuple(x.shape)}")
+    if torch.is_grad_enabled() and x.requires_grad:
+        raise NotImplementedError(f"{what}: backward through the B200 kernels (SURVEY.md §8a E8) is not implemented "
+                                  "yet; call under torch.no_grad()")
+
+
+def _to_bf16_2d(x: torch.Tensor) -> torch.Tensor:
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()          # e.g. the transposed view Image.PatchEmbed returns (Data2Seq/Image.py:26)
+    return x2 if x2.dtype == torch.bfloat16 else ops.cast(x2, torch.bfloat16)
+
+
+def _from_bf16(y2: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    y = y2 if like.dtype == torch.bfloat16 else ops.cast(y2, like.dtype)
+    return y.reshape(like.shape[:-1] + (y2.shape[-1],))
+
+
+class Mlp(nn.Module):
+    """timm 0.4.12 Mlp: fc2(drop(act(fc1(x)))) with one shared `drop` (mlp.py:11-35 in the OpenPoints copy)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+        if not isinstance(self.act, nn.GELU) or getattr(self.act, "approximate", "none") != "none":
+            raise NotImplementedError("Mlp: only act_layer=nn.GELU (exact erf) has a fused B200 epilogue")
+
+    def _check_train(self):
+        if self.training and self.drop.p > 0:
+            raise NotImplementedError("Mlp: dropout p > 0 in training mode is not implemented on the B200 path yet")
+
+    def _forward_2d(self, h: torch.Tensor, residual: Optional[torch.Tensor]) -> torch.Tensor:
+        w1 = _packed(self, "fc1.weight", self.fc1.weight, torch.bfloat16)
+        b1 = _packed(self, "fc1.bias", self.fc1.bias, torch.float32)
+        w2 = _packed(self, "fc2.weight", self.fc2.weight, torch.bfloat16)
+        b2 = _packed(self, "fc2.bias", self.fc2.bias, torch.float32)
+        hid = ops.linear(h, w1, b1, gelu=True)
+        return ops.linear(hid, w2, b2, residual=residual)
+
+    def forward(self, x):
+        _check_input(x, "Mlp")
+        self._check_train()
+        return _from_bf16(self._forward_2d(_to_bf16_2d(x), None), x)
+
+
+class Attention(nn.Module):
+    """timm 0.4.12 Attention (attention.py:12-38): qkv Linear -> softmax(q k^T * scale) v -> proj Linear."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        if dim % num_heads != 0:
+            raise ValueError("Attention: dim must be divisible by num_heads")
+
+    def _check_train(self):
+        if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
+            raise NotImplementedError("Attention: dropout p > 0 in training mode is not implemented on the B200 path yet")
+
+    def _forward_2d(self, h: torch.Tensor, B: int, N: int, residual: Optional[torch.Tensor]) -> torch.Tensor:
+        wq = _packed(self, "qkv.weight", self.qkv.weight, torch.bfloat16)
+        bq = _packed(self, "qkv.bias", self.qkv.bias, torch.float32)
+        wp = _packed(self, "proj.weight", self.proj.weight, torch.bfloat16)
+        bp = _packed(self, "proj.bias", self.proj.bias, torch.float32)
+        qkv = ops.linear(h, wq, bq)                                   # (M, 3C), packed (3, H, dh)
+        o = ops.attention(qkv.view(B, N, -1), self.num_heads, self.scale)   # (B, N, C)
+        return ops.linear(o.view(B * N, -1), wp, bp, residual=residual)
+
+    def forward(self, x):
+        _check_input(x, "Attention")
+        self._check_train()
+        B, N, C = x.shape
+        return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N, None), x)
+
+
+def _layernorm_eps(norm: nn.Module) -> float:
+    if not isinstance(norm, nn.LayerNorm) or not norm.elementwise_affine:
+        raise NotImplementedError("Block: only norm_layer=nn.LayerNorm (affine) has a B200 kernel")
+    return norm.eps
+
+
+class Block(nn.Module):
+    """timm Block: x = x + drop_path(attn(norm1(x))); x = x + drop_path(mlp(norm2(x)))  (attention.py:41-58).
+
+    Seven kernel launches per forward: LN, GEMM(qkv+bias), attention, GEMM(proj+bias+residual), LN,
+    GEMM(fc1+bias+GELU), GEMM(fc2+bias+residual).
+    """
+
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, qk_scale=None, drop=0., attn_drop=0.,
+                 drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm, init_values=None):
+        super().__init__()
+        if init_values is not None:
+            raise NotImplementedError("Block: layer-scale (init_values) is not part of the Meta-Transformer encoder")
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop,
+                              proj_drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        mlp_hidden_dim = int(dim * mlp_ratio)
+        self.mlp = Mlp(in_features=dim, hidden_features=mlp_hidden_dim, act_layer=act_layer, drop=drop)
+        _layernorm_eps(self.norm1)
+        _layernorm_eps(self.norm2)
+
+    def _forward_2d(self, x2: torch.Tensor, B: int, N: int) -> torch.Tensor:
+        g1 = _packed(self, "norm1.weight", self.norm1.weight, torch.float32)
+        b1 = _packed(self, "norm1.bias", self.norm1.bias, torch.float32)
+        g2 = _packed(self, "norm2.weight", self.norm2.weight, torch.float32)
+        b2 = _packed(self, "norm2.bias", self.norm2.bias, torch.float32)
+        h = ops.layernorm(x2, g1, b1, self.norm1.eps)
+        x_mid = self.attn._forward_2d(h, B, N, residual=x2)
+        h = ops.layernorm(x_mid, g2, b2, self.norm2.eps, out=h)
+        return self.mlp._forward_2d(h, residual=x_mid)
+
+    def forward(self, x):
+        _check_input(x, "Block")
+        self.attn._check_train()
+        self.mlp._check_train()
+        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
+            raise NotImplementedError("Block: drop_path > 0 in training mode is not implemented on the B200 path yet")
+        B, N, C = x.shape
+        return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N), x)

@@ -1,0 +1,64 @@
+"""World-size-2 gloo test of the data-parallel host logic: batch sharding and the bucketed
+gradient all-reduce used after backward.  Runs on CPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from metatransformer_b200.distributed import allreduce_gradients, shard_range
+
+
+def test_shard_range_partitions_batch():
+    for gb in (1, 7, 8, 256, 257):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(gb, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == gb
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Linear(32, 4))
+    model[1].weight.requires_grad_(False)          # frozen parameter: must be skipped
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(5, 16, generator=g)
+    model(x).square().mean().backward()
+    local = [p.grad.clone() for p in model.parameters() if p.grad is not None]
+    n = allreduce_gradients(model.parameters(), world, bucket_bytes=1024)
+    out = [p.grad.clone() for p in model.parameters() if p.grad is not None]
+    q.put((rank, n, local, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_allreduce_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=100) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, n0, l0, o0), (_, n1, l1, o1) = res
+    assert n0 == n1 and n0 >= 2                    # several 1 KB buckets
+    assert len(o0) == 3                            # weight0, bias0, bias1 (frozen weight has no grad)
+    for a, b, x, y in zip(l0, l1, o0, o1):
+        assert torch.allclose(x, (a + b) / 2, atol=1e-6) and torch.allclose(x, y)

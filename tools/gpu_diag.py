@@ -189,14 +189,35 @@ def group_perf():
     print(f"[perf] layernorm M={M} d=768: {ms:.4f} ms  {M * 768 * 4 / ms / 1e6:.1f} GB/s", flush=True)
 
 
-GROUPS = {"basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+def group_prof():
+    """tiny launch set for ncu: fc2-shaped GEMM, cg=1 then cg=2, plus attention and layernorm"""
+    import torch
+    from metatransformer_b200 import ops
+    dev = "cuda"
+    M, N, K = 50176, 768, 3072
+    x = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    b = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for cg in (1, 2):
+        for _ in range(2):
+            ops.linear(x, w, b, r, cta_group=cg, out=out)
+    torch.cuda.synchronize()
+    qkv = torch.randn(256, 196, 3 * 768, device=dev).bfloat16()
+    for _ in range(2):
+        ops.attention(qkv, 12)
+    torch.cuda.synchronize()
+
+
+GROUPS = {"prof": group_prof, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
 
 
 def main():
     if len(sys.argv) > 1 and sys.argv[1] in GROUPS:
         GROUPS[sys.argv[1]]()
         return
-    names = sys.argv[1:] if len(sys.argv) > 1 else list(GROUPS)
+    names = sys.argv[1:] if len(sys.argv) > 1 else [g for g in GROUPS if g != "prof"]
     outdir = ROOT / "gpurun_out" / "diag"
     outdir.mkdir(parents=True, exist_ok=True)
     for name in names:
