@@ -28,13 +28,14 @@ constexpr int kAtD = 64;                    // head dim
 constexpr int kAtStages = 3;
 constexpr int kAtThreads = 32 * (4 * kAtQT + 4);  // warps 10, 11 only pad the third warpgroup (setmaxnreg)
 constexpr int kAtTileBytes = 128 * 64 * 2;  // 16 KB: any 128 x 64 bf16 tile
+constexpr int kAtQBufs = 2;                 // Q tiles are double-buffered across work items
 constexpr int kAtSmemQ = 0;
-constexpr int kAtSmemK = kAtSmemQ + kAtQT * kAtTileBytes;
+constexpr int kAtSmemK = kAtSmemQ + kAtQBufs * kAtQT * kAtTileBytes;
 constexpr int kAtSmemV = kAtSmemK + kAtStages * kAtTileBytes;
 constexpr int kAtSmemP = kAtSmemV + kAtStages * kAtTileBytes;           // per q-tile: 2 chunks of 64 keys
 constexpr int kAtSmemBar = kAtSmemP + kAtQT * 2 * kAtTileBytes;
-// barriers: q_full[2] q_empty[2] k_full[3] k_empty[3] v_full[3] v_empty[3] s_full[2] s_empty[2] p_full[2] o_done[2]
-constexpr int kAtNumBars = 4 * kAtQT + 4 * kAtStages + 2 * kAtQT;
+// barriers: q_full[4] q_empty[4] k_full[3] k_empty[3] v_full[3] v_empty[3] s_full[2] s_empty[2] p_full[2] o_done[2]
+constexpr int kAtNumBars = 2 * kAtQBufs * kAtQT + 4 * kAtStages + 4 * kAtQT;
 constexpr int kAtSmemTmemPtr = kAtSmemBar + kAtNumBars * 8;
 constexpr int kAtSmemBytes = kAtSmemTmemPtr + 16 + 1024;
 constexpr int kAtTmemCols = 512;
@@ -65,16 +66,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const int lane = threadIdx.x & 31;
 
   const uint32_t bar0 = smem_base + kAtSmemBar;
-  auto q_full = [&](int t) { return bar0 + 8u * (0 + t); };
-  auto q_empty = [&](int t) { return bar0 + 8u * (2 + t); };
-  auto k_full = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (7 + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (10 + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (13 + s); };
-  auto s_full = [&](int t) { return bar0 + 8u * (16 + t); };
-  auto s_empty = [&](int t) { return bar0 + 8u * (18 + t); };
-  auto p_full = [&](int t) { return bar0 + 8u * (20 + t); };
-  auto o_done = [&](int t) { return bar0 + 8u * (22 + t); };
+  auto q_full = [&](int qb, int t) { return bar0 + 8u * (0 + 2 * qb + t); };
+  auto q_empty = [&](int qb, int t) { return bar0 + 8u * (4 + 2 * qb + t); };
+  auto k_full = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (11 + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (14 + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (17 + s); };
+  auto s_full = [&](int t) { return bar0 + 8u * (20 + t); };
+  auto s_empty = [&](int t) { return bar0 + 8u * (22 + t); };
+  auto p_full = [&](int t) { return bar0 + 8u * (24 + t); };
+  auto o_done = [&](int t) { return bar0 + 8u * (26 + t); };
+  auto q_smem = [&](int qb, int t) { return smem_base + uint32_t(kAtSmemQ + (2 * qb + t) * kAtTileBytes); };
   const uint32_t tmem_ptr_addr = smem_base + kAtSmemTmemPtr;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kAtSmemTmemPtr);
 
@@ -82,8 +84,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_out);
     for (int t = 0; t < kAtQT; ++t) {
-      mbar_init(q_full(t), 1);
-      mbar_init(q_empty(t), 1);
+      for (int qb = 0; qb < kAtQBufs; ++qb) {
+        mbar_init(q_full(qb, t), 1);
+        mbar_init(q_empty(qb, t), 1);
+      }
       mbar_init(s_full(t), 1);
       mbar_init(s_empty(t), 4);  // one arrive per softmax warp
       mbar_init(p_full(t), 4);
@@ -120,11 +124,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         const int qp = item % p.num_qp;
         const int bh = item / p.num_qp;
         const int h = bh % H, b = bh / H;
+        const int qb = int(it & 1u);
         for (int t = 0; t < kAtQT; ++t) {
-          mbar_wait(q_empty(t), (it & 1u) ^ 1u);
-          mbar_arrive_expect_tx(q_full(t), kAtTileBytes);
-          tma_load_4d(smem_base + kAtSmemQ + t * kAtTileBytes, &tm_qkv, q_full(t), 0, h, qp * 256 + t * 128, b,
-                      kEvictFirst);
+          mbar_wait(q_empty(qb, t), ((it >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(q_full(qb, t), kAtTileBytes);
+          tma_load_4d(q_smem(qb, t), &tm_qkv, q_full(qb, t), 0, h, qp * 256 + t * 128, b, kEvictFirst);
         }
         for (int j = 0; j < p.num_kv; ++j) {
           mbar_wait(k_empty(kst), kph ^ 1u);
@@ -151,11 +155,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       uint32_t n_p[kAtQT] = {0, 0};  // P_t tiles consumed so far
       uint32_t it = 0;
 
-      auto issue_s = [&](int t, int kstage) {
+      auto issue_s = [&](int t, int qb, int kstage) {
         // wait until the softmax warps pulled the previous S_t out of TMEM
         mbar_wait(s_empty(t), (n_s[t] & 1u) ^ 1u);
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc_sw128(smem_base + kAtSmemQ + t * kAtTileBytes);
+        const uint64_t adesc = make_smem_desc_sw128(q_smem(qb, t));
         const uint64_t bdesc = make_smem_desc_sw128(smem_base + kAtSmemK + kstage * kAtTileBytes);
 #pragma unroll
         for (int k = 0; k < kAtD / 16; ++k)
@@ -165,25 +169,33 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         ++n_s[t];
       };
 
+      // Issue order per KV step: P0·V, next S0, P1·V, next S1 — where "next S" is the following KV tile of this item
+      // or, on the last tile, the FIRST tile of the next work item (its Q sits in the other Q buffer), so the softmax
+      // warps never wait for a cold pipeline between items.
+      bool first = true;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        // ---- prologue: S_t(0) for both query tiles ----
-        mbar_wait(k_full(kst), kph);
+        const int qb = int(it & 1u);
+        const bool has_next_item = (item + int(gridDim.x) < p.num_items);
+        if (first) {
+          first = false;
+          mbar_wait(k_full(kst), kph);
 #pragma unroll
-        for (int t = 0; t < kAtQT; ++t) {
-          mbar_wait(q_full(t), it & 1u);
-          tc_fence_after();
-          issue_s(t, kst);
-          if (p.num_kv == 1) umma_commit(q_empty(t));
+          for (int t = 0; t < kAtQT; ++t) {
+            mbar_wait(q_full(qb, t), (it >> 1) & 1u);
+            tc_fence_after();
+            issue_s(t, qb, kst);
+            if (p.num_kv == 1) umma_commit(q_empty(qb, t));
+          }
+          umma_commit(k_empty(kst));
+          if (++kst == kAtStages) { kst = 0; kph ^= 1u; }
         }
-        umma_commit(k_empty(kst));
-        if (++kst == kAtStages) { kst = 0; kph ^= 1u; }
-
         for (int j = 0; j < p.num_kv; ++j) {
           const int valid = min(kAtBN, p.N - j * kAtBN);
           const int ksteps = 2 * ((valid + 31) / 32);  // 16-key steps covering the valid 32-key chunks
           const bool more = (j + 1 < p.num_kv);
+          const bool next_s = more || has_next_item;
           mbar_wait(v_full(vst), vph);
-          if (more) mbar_wait(k_full(kst), kph);
+          if (next_s) mbar_wait(k_full(kst), kph);
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
             // ---- O_t (+)= P_t(j) V_j ----
@@ -198,18 +210,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
               umma_f16_ss<1>(tmem_base + kAtTmemO + t * kAtD, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(o_done(t));
-            if (t == kAtQT - 1) {
-              umma_commit(v_empty(vst));
-            }
-            // ---- S_t(j+1) ----
+            if (t == kAtQT - 1) umma_commit(v_empty(vst));
+            // ---- next S_t ----
             if (more) {
-              issue_s(t, kst);
-              if (j + 2 == p.num_kv) umma_commit(q_empty(t));  // last use of Q_t for this item
-              if (t == kAtQT - 1) umma_commit(k_empty(kst));
+              issue_s(t, qb, kst);
+              if (j + 2 == p.num_kv) umma_commit(q_empty(qb, t));  // last use of Q_t for this item
+            } else if (has_next_item) {
+              const uint32_t nit = it + 1;
+              mbar_wait(q_full(int(nit & 1u), t), (nit >> 1) & 1u);
+              tc_fence_after();
+              issue_s(t, int(nit & 1u), kst);
+              if (p.num_kv == 1) umma_commit(q_empty(int(nit & 1u), t));
             }
+            if (next_s && t == kAtQT - 1) umma_commit(k_empty(kst));
           }
           if (++vst == kAtStages) { vst = 0; vph ^= 1u; }
-          if (more) { if (++kst == kAtStages) { kst = 0; kph ^= 1u; } }
+          if (next_s) { if (++kst == kAtStages) { kst = 0; kph ^= 1u; } }
         }
       }
     }

@@ -19,6 +19,7 @@
 // warp 3 idle, warps 4..11 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half).
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
+#include <stdlib.h>
 
 namespace mt {
 
@@ -104,7 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), CG);   // leader: arrive.expect_tx, peer: remote arrive
+      mbar_init(full_bar(s), 1);    // one arrive.expect_tx (leader CTA) + the TMA bytes of both CTAs
       mbar_init(empty_bar(s), 1);   // one tcgen05.commit per use
     }
     for (int s = 0; s < kAccStages; ++s) {
@@ -139,8 +140,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t sb = sa + Cfg::kABytes;
           if constexpr (CG == 2) {
             const uint32_t fb = full_leader_base + 8u * stage;
+            // Only the leader arms its barrier, for the bytes of BOTH CTAs.  The peer's complete_tx may land before
+            // the leader's expect_tx of the same phase (tx-count goes transiently negative, which is legal); it can
+            // never land in a later phase because the peer only re-uses a slot after the leader's MMA consumed it.
             if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg::kStageBytes);
-            else mbar_arrive_remote(full_bar(stage), 0);
             tma_load_2d_cg2(sa, &tm_a, fb, kb * kBK, row_a, kEvictNormal);
             tma_load_2d_cg2(sb, &tm_b, fb, kb * kBK, row_b, kEvictLast);
           } else {
@@ -378,8 +381,17 @@ extern "C" int mt_gemm_bf16(const void* x, const void* w, const float* bias, con
              MT_ERR_BAD_ALIGN, "mt_gemm_bf16: all pointers must be 16-byte aligned");
   MT_REQUIRE(act == 0 || act == 1, MT_ERR_UNSUPPORTED, "mt_gemm_bf16: act must be 0 (none) or 1 (gelu)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cta_group == 0) {
+    // auto: CTA pairs unless overridden (MT_B200_GEMM_CG=1|2, read once; for A/B experiments only)
+    static int auto_cg = 0;
+    if (auto_cg == 0) {
+      const char* e = getenv("MT_B200_GEMM_CG");
+      auto_cg = (e && e[0] == '1') ? 1 : 2;
+    }
+    cta_group = auto_cg;
+  }
   if (cta_group == 1) return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, s);
-  if (cta_group == 2 || cta_group == 0) return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, s);
+  if (cta_group == 2) return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, s);
   set_error("mt_gemm_bf16: cta_group must be 0 (auto), 1 or 2");
   return MT_ERR_UNSUPPORTED;
 }

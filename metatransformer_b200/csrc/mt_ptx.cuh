@@ -64,7 +64,7 @@ MT_DEVINL void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
 MT_DEVINL uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
