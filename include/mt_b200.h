@@ -46,6 +46,19 @@ int mt_device_ok(int device);         /* 0 if `device` is compute capability 10.
 int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
                  int M, int N, int K, int act, int cta_group, void* stream);
 
+/* ---- E2+E3 / E2+E6 fused: Linear(LayerNorm(x)) with the LayerNorm folded into the GEMM ------------------------
+ * LN(x) W^T + b = rstd_m * (x W'^T - mean_m * colsum_n) + b'_n  with  W' = W*gamma (bf16), colsum_n = sum_k W'[n,k],
+ * b' = b + W beta  (prepared once by mt_fold_layernorm) and per-row (mean, rstd) from mt_row_stats.  The
+ * normalised activations never exist in HBM.  Same reference spans as mt_layernorm + mt_gemm_bf16
+ * (attention.py:56 `attn(norm1(x))` -> qkv, :57 `mlp(norm2(x))` -> fc1).                                      */
+int mt_row_stats(const void* x, int x_dtype, float* stats /* [M][2] = mean, rstd */, int M, int d, float eps,
+                 void* stream);
+int mt_fold_layernorm(const void* w /* [N,K] */, int w_dtype, const float* gamma, const float* beta,
+                      const float* bias /* [N] or NULL */, void* w_folded /* bf16 [N,K] */, float* colsum /* [N] */,
+                      float* bias_folded /* [N] */, int N, int K, void* stream);
+int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float* bias_folded, const float* colsum,
+                    const float* row_stats, void* y, int M, int N, int K, int act, int cta_group, void* stream);
+
 /* ---- E2: LayerNorm over the last dim, fp32 statistics, biased variance -------------------------------------
  * y[M,d] (bf16) = (x - mean) * rsqrt(var + eps) * gamma + beta;  x bf16 or fp32 (x_dtype), gamma/beta fp32.
  * Replaces norm1 / norm2 = nn.LayerNorm(d) of Block (attention.py:46,50; eps 1e-5 per README.md:131).       */
@@ -81,6 +94,10 @@ typedef struct {
   const float* ln2_w; const float* ln2_b;      /* [d]            norm2                    */
   const void* fc1_w;  const float* fc1_b;      /* [hidden,d], [hidden] */
   const void* fc2_w;  const float* fc2_b;      /* [d,hidden], [d]      */
+  /* Optional LN folding: when both are non-NULL, qkv_w/qkv_b and fc1_w/fc1_b hold the outputs of mt_fold_layernorm
+   * (W*gamma, b + W beta) and these are the matching column sums; ln*_w / ln*_b are then unused.              */
+  const float* qkv_colsum;                      /* [3d] or NULL */
+  const float* fc1_colsum;                      /* [hidden] or NULL */
 } mt_block_weights;
 
 int mt_encoder_create(mt_encoder** out, int dim, int heads, int hidden, int depth, float eps,

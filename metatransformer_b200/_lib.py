@@ -16,7 +16,8 @@ LIB_PATH = _PKG / "lib" / "libmt_b200.so"
 MT_DT_BF16, MT_DT_F32, MT_DT_F16 = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
-    "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_layernorm", "mt_attention_fwd",
+    "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_gemm_bf16_ln", "mt_row_stats",
+    "mt_fold_layernorm", "mt_layernorm", "mt_attention_fwd",
     "mt_im2row", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
     "mt_encoder_forward", "mt_encoder_launches_per_forward",
 )
@@ -35,6 +36,7 @@ class BlockWeights(Structure):
         ("ln2_w", c_void_p), ("ln2_b", c_void_p),
         ("fc1_w", c_void_p), ("fc1_b", c_void_p),
         ("fc2_w", c_void_p), ("fc2_b", c_void_p),
+        ("qkv_colsum", c_void_p), ("fc1_colsum", c_void_p),
     ]
 
 
@@ -51,6 +53,13 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_gemm_bf16.restype = c_int
     lib.mt_gemm_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]
+    lib.mt_gemm_bf16_ln.restype = c_int
+    lib.mt_gemm_bf16_ln.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
+    lib.mt_row_stats.restype = c_int
+    lib.mt_row_stats.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p]
+    lib.mt_fold_layernorm.restype = c_int
+    lib.mt_fold_layernorm.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_void_p]
     lib.mt_layernorm.restype = c_int
     lib.mt_layernorm.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]
     lib.mt_attention_fwd.restype = c_int

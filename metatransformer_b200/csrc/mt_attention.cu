@@ -169,7 +169,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         ++n_s[t];
       };
 
-      // Issue order per KV step: P0·V, next S0, P1·V, next S1 — where "next S" is the following KV tile of this item
+      // Issue order per KV step: next S0, next S1, P0·V, P1·V — where "next S" is the following KV tile of this item
       // or, on the last tile, the FIRST tile of the next work item (its Q sits in the other Q buffer), so the softmax
       // warps never wait for a cold pipeline between items.
       bool first = true;
@@ -196,6 +196,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           const bool next_s = more || has_next_item;
           mbar_wait(v_full(vst), vph);
           if (next_s) mbar_wait(k_full(kst), kph);
+          // ---- next S_t first: it only needs the softmax warps to have pulled S_t(j) into registers, so the tensor
+          //      core produces the next scores while the softmax warps are still exponentiating the current ones ----
+          if (next_s) {
+#pragma unroll
+            for (int t = 0; t < kAtQT; ++t) {
+              if (more) {
+                issue_s(t, qb, kst);
+                if (j + 2 == p.num_kv) umma_commit(q_empty(qb, t));  // last use of Q_t for this item
+              } else {
+                const uint32_t nit = it + 1;
+                mbar_wait(q_full(int(nit & 1u), t), (nit >> 1) & 1u);
+                tc_fence_after();
+                issue_s(t, int(nit & 1u), kst);
+                if (p.num_kv == 1) umma_commit(q_empty(int(nit & 1u), t));
+              }
+            }
+            umma_commit(k_empty(kst));
+          }
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
             // ---- O_t (+)= P_t(j) V_j ----
@@ -211,18 +229,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             }
             umma_commit(o_done(t));
             if (t == kAtQT - 1) umma_commit(v_empty(vst));
-            // ---- next S_t ----
-            if (more) {
-              issue_s(t, qb, kst);
-              if (j + 2 == p.num_kv) umma_commit(q_empty(qb, t));  // last use of Q_t for this item
-            } else if (has_next_item) {
-              const uint32_t nit = it + 1;
-              mbar_wait(q_full(int(nit & 1u), t), (nit >> 1) & 1u);
-              tc_fence_after();
-              issue_s(t, int(nit & 1u), kst);
-              if (p.num_kv == 1) umma_commit(q_empty(int(nit & 1u), t));
-            }
-            if (next_s && t == kAtQT - 1) umma_commit(k_empty(kst));
           }
           if (++vst == kAtStages) { vst = 0; vph ^= 1u; }
           if (next_s) { if (++kst == kAtStages) { kst = 0; kph ^= 1u; } }
@@ -255,16 +261,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
       for (int j = 0; j < p.num_kv; ++j) {
         const int valid = min(kAtBN, p.N - j * kAtBN);
-        const int nch = (valid + 31) >> 5;  // 32-key chunks that hold at least one valid key
-        const bool need_mask = (valid & 31) != 0;
+        const int nfull = valid >> 5;        // 32-key chunks without padding
+        const int tail = valid & 31;         // valid keys of the last, partially padded chunk (0 = none)
         mbar_wait(s_full(t), n_sf & 1u);
         ++n_sf;
         tc_fence_after();
         uint32_t s[128];
-        tmem_ld_32x32b_x32_at<0>(ts, s);
-        if (nch > 1) tmem_ld_32x32b_x32_at<32>(ts + 32u, s);
-        if (nch > 2) tmem_ld_32x32b_x32_at<64>(ts + 64u, s);
-        if (nch > 3) tmem_ld_32x32b_x32_at<96>(ts + 96u, s);
+        // the padded chunk (runtime TMEM column 32*nfull) always lands in s[96..127]: that slot is only needed by a
+        // fourth full chunk, and then there is no padded chunk
+        if (nfull > 0) tmem_ld_32x32b_x32_at<0>(ts, s);
+        if (nfull > 1) tmem_ld_32x32b_x32_at<32>(ts + 32u, s);
+        if (nfull > 2) tmem_ld_32x32b_x32_at<64>(ts + 64u, s);
+        if (nfull > 3) tmem_ld_32x32b_x32_at<96>(ts + 96u, s);
+        if (tail) tmem_ld_32x32b_x32_at<96>(ts + uint32_t(32 * nfull), s);
         tmem_wait_ld();
         // S_t is in registers: the tensor core may overwrite it with the next tile's scores
         tc_fence_before();
@@ -275,16 +284,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         float m_tile = -INFINITY;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          if (ch < nch) {
+          if (ch < nfull) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float v = __uint_as_float(s[32 * ch + i]);
-              if (need_mask && ch == nch - 1) {  // warp-uniform: only the last chunk can hold padded keys
-                v = (32 * ch + i < valid) ? v : -INFINITY;
-                s[32 * ch + i] = __float_as_uint(v);
-              }
-              m_tile = fmaxf(m_tile, v);
-            }
+            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(s[32 * ch + i]));
+          }
+        }
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = (i < tail) ? __uint_as_float(s[96 + i]) : -INFINITY;   // padded keys (zero K rows) -> -inf
+            s[96 + i] = __float_as_uint(v);
+            m_tile = fmaxf(m_tile, v);
           }
         }
         const float m_new = fmaxf(m_run, m_tile);
@@ -320,7 +330,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         float l_tile = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          if (ch < nch) {
+          if (ch < nfull) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {  // four 16-byte groups (8 keys each) per 32-key chunk
               uint32_t pk[4];
@@ -337,6 +347,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                            "r"(pk[3])
                            : "memory");
             }
+          }
+        }
+        if (tail) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(s[96 + 8 * g + 2 * i]), c, -mc));   // exp2(-inf) = 0
+              const float e1 = ex2_approx(fmaf(__uint_as_float(s[96 + 8 * g + 2 * i + 1]), c, -mc));
+              l_tile += e0 + e1;
+              pk[i] = pack_bf16x2(e0, e1);
+            }
+            const uint32_t chunk16 = uint32_t((nfull & 1) * 4 + g);
+            const uint32_t addr = prow + uint32_t((nfull >> 1) * kAtTileBytes) + ((chunk16 ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                         "r"(pk[3])
+                         : "memory");
           }
         }
         l_run = fmaf(l_run, alpha, l_tile);

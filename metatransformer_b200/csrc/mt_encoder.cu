@@ -4,6 +4,8 @@
 //   Block.forward: x = x + attn(norm1(x)); x = x + mlp(norm2(x))   (PointCloud/.../layers/attention.py:55-58)
 // run as 7 launches per Block on one stream with caller-provided scratch, instead of ~15 eager kernels:
 //   LN1 -> GEMM(qkv,+bias) -> attention -> GEMM(proj,+bias,+x) -> LN2 -> GEMM(fc1,+bias,GELU) -> GEMM(fc2,+bias,+x)
+// With folded weights (mt_fold_layernorm) the two LN launches shrink to row-statistics passes (read-only) and the
+// normalisation itself happens in the qkv / fc1 GEMM epilogues.
 #include "mt_common.cuh"
 #include <vector>
 #include <new>
@@ -16,7 +18,7 @@ struct mt_encoder {
 
 namespace {
 struct WsLayout {
-  size_t h, qkv, attn, mid, xo0, xo1, hid, total;
+  size_t h, qkv, attn, mid, xo0, xo1, hid, stats, total;
 };
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 WsLayout ws_layout(const mt_encoder* e, size_t M) {
@@ -30,6 +32,7 @@ WsLayout ws_layout(const mt_encoder* e, size_t M) {
   w.xo0 = take(M * e->dim);
   w.xo1 = take(M * e->dim);
   w.hid = take(M * e->hidden);
+  w.stats = take(M * 4);  // float2 per row
   w.total = off;
   return w;
 }
@@ -45,8 +48,12 @@ extern "C" int mt_encoder_create(mt_encoder** out, int dim, int heads, int hidde
   MT_REQUIRE(dim % 32 == 0 && hidden % 32 == 0, MT_ERR_BAD_SHAPE, "mt_encoder_create: dim/hidden must be multiples of 32");
   for (int l = 0; l < depth; ++l) {
     const mt_block_weights& b = blocks[l];
-    MT_REQUIRE(b.ln1_w && b.ln1_b && b.qkv_w && b.proj_w && b.ln2_w && b.ln2_b && b.fc1_w && b.fc2_w, MT_ERR_BAD_SHAPE,
+    MT_REQUIRE(b.qkv_w && b.proj_w && b.fc1_w && b.fc2_w, MT_ERR_BAD_SHAPE,
                "mt_encoder_create: block %d has a null weight pointer", l);
+    MT_REQUIRE((b.qkv_colsum != nullptr) == (b.fc1_colsum != nullptr), MT_ERR_BAD_SHAPE,
+               "mt_encoder_create: block %d: fold both LayerNorms or none", l);
+    MT_REQUIRE(b.qkv_colsum || (b.ln1_w && b.ln1_b && b.ln2_w && b.ln2_b), MT_ERR_BAD_SHAPE,
+               "mt_encoder_create: block %d has neither folded weights nor LayerNorm parameters", l);
   }
   mt_encoder* e = new (std::nothrow) mt_encoder;
   MT_REQUIRE(e, MT_ERR_CUDA, "mt_encoder_create: out of host memory");
@@ -90,6 +97,7 @@ extern "C" int mt_encoder_forward(mt_encoder* enc, const void* x, void* y, int B
   void* mid = ws + w.mid;
   void* xo[2] = {ws + w.xo0, ws + w.xo1};
   void* hid = ws + w.hid;
+  float* stats = reinterpret_cast<float*>(ws + w.stats);
   const int d = enc->dim;
   const float scale = 0.125f;  // head_dim^-0.5 with head_dim = 64
   const void* cur = x;
@@ -97,12 +105,23 @@ extern "C" int mt_encoder_forward(mt_encoder* enc, const void* x, void* y, int B
     const mt_block_weights& bw = enc->blocks[l];
     void* outp = (l == enc->depth - 1) ? y : xo[l & 1];
     int rc;
-    if ((rc = mt_layernorm(cur, MT_DT_BF16, bw.ln1_w, bw.ln1_b, h, M, d, enc->eps, stream))) return rc;
-    if ((rc = mt_gemm_bf16(h, bw.qkv_w, bw.qkv_b, nullptr, qkv, M, 3 * d, d, 0, 0, stream))) return rc;
+    if (bw.qkv_colsum) {
+      if ((rc = mt_row_stats(cur, MT_DT_BF16, stats, M, d, enc->eps, stream))) return rc;
+      if ((rc = mt_gemm_bf16_ln(cur, bw.qkv_w, bw.qkv_b, bw.qkv_colsum, stats, qkv, M, 3 * d, d, 0, 0, stream))) return rc;
+    } else {
+      if ((rc = mt_layernorm(cur, MT_DT_BF16, bw.ln1_w, bw.ln1_b, h, M, d, enc->eps, stream))) return rc;
+      if ((rc = mt_gemm_bf16(h, bw.qkv_w, bw.qkv_b, nullptr, qkv, M, 3 * d, d, 0, 0, stream))) return rc;
+    }
     if ((rc = mt_attention_fwd(qkv, attn, B, N, enc->heads, 64, scale, stream))) return rc;
     if ((rc = mt_gemm_bf16(attn, bw.proj_w, bw.proj_b, cur, mid, M, d, d, 0, 0, stream))) return rc;
-    if ((rc = mt_layernorm(mid, MT_DT_BF16, bw.ln2_w, bw.ln2_b, h, M, d, enc->eps, stream))) return rc;
-    if ((rc = mt_gemm_bf16(h, bw.fc1_w, bw.fc1_b, nullptr, hid, M, enc->hidden, d, 1, 0, stream))) return rc;
+    if (bw.fc1_colsum) {
+      if ((rc = mt_row_stats(mid, MT_DT_BF16, stats, M, d, enc->eps, stream))) return rc;
+      if ((rc = mt_gemm_bf16_ln(mid, bw.fc1_w, bw.fc1_b, bw.fc1_colsum, stats, hid, M, enc->hidden, d, 1, 0, stream)))
+        return rc;
+    } else {
+      if ((rc = mt_layernorm(mid, MT_DT_BF16, bw.ln2_w, bw.ln2_b, h, M, d, enc->eps, stream))) return rc;
+      if ((rc = mt_gemm_bf16(h, bw.fc1_w, bw.fc1_b, nullptr, hid, M, enc->hidden, d, 1, 0, stream))) return rc;
+    }
     if ((rc = mt_gemm_bf16(hid, bw.fc2_w, bw.fc2_b, mid, outp, M, d, enc->hidden, 0, 0, stream))) return rc;
     cur = outp;
   }

@@ -32,7 +32,7 @@ constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kBN;  // 512
 constexpr int kEpiStageBytes = 32 * 128;     // per-warp staging: 32 rows x 64 bf16
-constexpr int kBiasBytes = 128 * 4;          // per-warp bias slice: 128 fp32
+constexpr int kBiasBytes = 2 * 128 * 4;      // per-warp slices: 128 fp32 bias + 128 fp32 LN-fold column sums
 
 template <int CG>
 struct GemmCfg {
@@ -56,6 +56,9 @@ struct GemmParams {
   int M, N, K;
   int act;                      // 0 = identity, 1 = exact-erf GELU
   int num_m_tiles, num_n_tiles;
+  // LayerNorm folded into the GEMM (see mt_fold_layernorm): y = rstd_m * (acc - mean_m * colsum_n) + bias_n
+  const float2* row_stats;      // [M] (mean, rstd) or nullptr
+  const float* colsum;          // [N] sum_k W'[n,k] (of the bf16-rounded folded weight) or nullptr
 };
 
 // gelu(x) = x * Phi(x) with the exact (erf) definition, nn.GELU() default.
@@ -203,32 +206,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int row0 = m_tile * (kBM * CG) + int(rank) * kBM + 32 * q;  // first row of this warp
       const int col0 = n_tile * kBN + 128 * hf;                          // first column of this warp
       const int row = row0 + lane;
-      // bias slice for this warp's 128 columns -> private smem (float4 per lane)
+      // bias (and LN-fold column-sum) slices for this warp's 128 columns -> private smem (float4 per lane)
+      float ln_rstd = 1.f, ln_nmr = 0.f;  // rstd and -mean*rstd of this thread's row
       {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const int c = col0 + 4 * lane;
         if (p.bias != nullptr && c < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + c);
+        if (p.colsum != nullptr && c < p.N) c4 = *reinterpret_cast<const float4*>(p.colsum + c);
         __syncwarp();
         reinterpret_cast<float4*>(bias_s)[lane] = b4;
+        reinterpret_cast<float4*>(bias_s)[32 + lane] = c4;
         __syncwarp();
+        if (p.row_stats != nullptr && row < p.M) {
+          const float2 st = p.row_stats[row];
+          ln_rstd = st.y;
+          ln_nmr = -st.x * st.y;
+        }
       }
+      // residual slices are fetched one 32-column slice ahead of their use (the first one before the accumulator
+      // is even ready), so the L2/HBM latency hides behind the MMAs of this tile and the math of the previous slice
+      const bool row_ok = (p.resid != nullptr) && (row < p.M);
+      const __nv_bfloat16* rrow = row_ok ? p.resid + size_t(row) * p.ldr : nullptr;
+      uint4 rv_next[4];
+      auto load_resid = [&](int sc_, uint4 (&dst)[4]) {
+        const int c_ = col0 + 32 * sc_;
+        if (row_ok && c_ < p.N) {
+          const uint4* rp = reinterpret_cast<const uint4*>(rrow + c_);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = __ldg(rp + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      load_resid(0, rv_next);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(32 * q) << 16) + uint32_t(as * kBN + 128 * hf);
 #pragma unroll 1
       for (int sc = 0; sc < 4; ++sc) {  // four 32-column slices; two slices = one 64-column TMA store
         const int c_sc = col0 + 32 * sc;
-        // residual slice (64 B per row) — issued before the TMEM load so the latency overlaps
         uint4 rv[4];
-        const bool has_res = (p.resid != nullptr) && (row < p.M) && (c_sc < p.N);
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + size_t(row) * p.ldr + c_sc);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = __ldg(rp + j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
-        }
+        for (int j = 0; j < 4; ++j) rv[j] = rv_next[j];
+        if (sc < 3) load_resid(sc + 1, rv_next);
         uint32_t acc[32];
         tmem_ld_32x32b_x32(t_row + uint32_t(32 * sc), acc);
         tmem_wait_ld();
@@ -251,10 +272,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = reinterpret_cast<const float4*>(bias_s)[8 * sc + j];
-          float v0 = __uint_as_float(acc[4 * j + 0]) + b4.x;
-          float v1 = __uint_as_float(acc[4 * j + 1]) + b4.y;
-          float v2 = __uint_as_float(acc[4 * j + 2]) + b4.z;
-          float v3 = __uint_as_float(acc[4 * j + 3]) + b4.w;
+          const float4 c4 = reinterpret_cast<const float4*>(bias_s)[32 + 8 * sc + j];
+          // rstd*(acc - mean*colsum) + bias; without LN folding rstd = 1 and colsum = 0: plain acc + bias
+          float v0 = fmaf(__uint_as_float(acc[4 * j + 0]), ln_rstd, fmaf(ln_nmr, c4.x, b4.x));
+          float v1 = fmaf(__uint_as_float(acc[4 * j + 1]), ln_rstd, fmaf(ln_nmr, c4.y, b4.y));
+          float v2 = fmaf(__uint_as_float(acc[4 * j + 2]), ln_rstd, fmaf(ln_nmr, c4.z, b4.z));
+          float v3 = fmaf(__uint_as_float(acc[4 * j + 3]), ln_rstd, fmaf(ln_nmr, c4.w, b4.w));
           if (p.act == 1) {
             v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
           }
@@ -302,7 +325,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 template <int CG>
 static int launch_gemm(const void* x, const void* w, const float* bias, const void* resid, int ldr, void* y, int M,
-                       int N, int K, int act, cudaStream_t stream) {
+                       int N, int K, int act, const float* row_stats, const float* colsum, cudaStream_t stream) {
   using Cfg = GemmCfg<CG>;
   CUtensorMap tm_a, tm_b, tm_y;
   {
@@ -332,6 +355,8 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   p.ldr = ldr;
   p.M = M; p.N = N; p.K = K;
   p.act = act;
+  p.row_stats = reinterpret_cast<const float2*>(row_stats);
+  p.colsum = colsum;
   p.num_m_tiles = ceil_div(M, kBM * CG);
   p.num_n_tiles = ceil_div(N, kBN);
 
@@ -367,19 +392,23 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
 
 }  // namespace mt
 
-extern "C" int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int M,
-                            int N, int K, int act, int cta_group, void* stream) {
+static int gemm_entry(const char* who, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                      int M, int N, int K, int act, const float* row_stats, const float* colsum, int cta_group,
+                      void* stream) {
   using namespace mt;
-  MT_REQUIRE(x && w && y, MT_ERR_BAD_SHAPE, "mt_gemm_bf16: null pointer");
-  MT_REQUIRE(M > 0 && N > 0 && K > 0, MT_ERR_BAD_SHAPE, "mt_gemm_bf16: M,N,K must be positive (got %d,%d,%d)", M, N, K);
+  MT_REQUIRE(x && w && y, MT_ERR_BAD_SHAPE, "%s: null pointer", who);
+  MT_REQUIRE(M > 0 && N > 0 && K > 0, MT_ERR_BAD_SHAPE, "%s: M,N,K must be positive (got %d,%d,%d)", who, M, N, K);
   MT_REQUIRE(K % 8 == 0 && N % 8 == 0, MT_ERR_BAD_SHAPE,
-             "mt_gemm_bf16: K and N must be multiples of 8 (16-byte rows for TMA); got K=%d N=%d", K, N);
-  MT_REQUIRE(N % 32 == 0, MT_ERR_BAD_SHAPE, "mt_gemm_bf16: N must be a multiple of 32 (got %d)", N);
+             "%s: K and N must be multiples of 8 (16-byte rows for TMA); got K=%d N=%d", who, K, N);
+  MT_REQUIRE(N % 32 == 0, MT_ERR_BAD_SHAPE, "%s: N must be a multiple of 32 (got %d)", who, N);
   MT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
-             MT_ERR_BAD_ALIGN, "mt_gemm_bf16: all pointers must be 16-byte aligned");
-  MT_REQUIRE(act == 0 || act == 1, MT_ERR_UNSUPPORTED, "mt_gemm_bf16: act must be 0 (none) or 1 (gelu)");
+                 (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(colsum) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(row_stats) & 7) == 0,
+             MT_ERR_BAD_ALIGN, "%s: all pointers must be 16-byte aligned", who);
+  MT_REQUIRE(act == 0 || act == 1, MT_ERR_UNSUPPORTED, "%s: act must be 0 (none) or 1 (gelu)", who);
+  MT_REQUIRE((row_stats == nullptr) == (colsum == nullptr), MT_ERR_BAD_SHAPE,
+             "%s: row_stats and colsum must be given together", who);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (cta_group == 0) {
     // auto: CTA pairs unless overridden (MT_B200_GEMM_CG=1|2, read once; for A/B experiments only)
@@ -390,8 +419,24 @@ extern "C" int mt_gemm_bf16(const void* x, const void* w, const float* bias, con
     }
     cta_group = auto_cg;
   }
-  if (cta_group == 1) return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, s);
-  if (cta_group == 2) return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, s);
-  set_error("mt_gemm_bf16: cta_group must be 0 (auto), 1 or 2");
+  if (cta_group == 1) return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, s);
+  if (cta_group == 2) return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, s);
+  set_error("%s: cta_group must be 0 (auto), 1 or 2", who);
   return MT_ERR_UNSUPPORTED;
+}
+
+extern "C" int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int M,
+                            int N, int K, int act, int cta_group, void* stream) {
+  return gemm_entry("mt_gemm_bf16", x, w, bias, residual, y, M, N, K, act, nullptr, nullptr, cta_group, stream);
+}
+
+extern "C" int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float* bias_folded, const float* colsum,
+                               const float* row_stats, void* y, int M, int N, int K, int act, int cta_group,
+                               void* stream) {
+  if (!row_stats || !colsum) {
+    mt::set_error("mt_gemm_bf16_ln: row_stats and colsum are required");
+    return MT_ERR_BAD_SHAPE;
+  }
+  return gemm_entry("mt_gemm_bf16_ln", x, w_folded, bias_folded, nullptr, y, M, N, K, act, row_stats, colsum, cta_group,
+                    stream);
 }

@@ -107,6 +107,65 @@ layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma, con
   }
 }
 
+// Row statistics only: stats[row] = (mean, rstd).  Feeds the LN-folded GEMM epilogue (mt_gemm_bf16_ln), which
+// makes the normalised activations never touch HBM.  Algorithmic traffic: M*d*sizeof(in) + 8*M bytes.
+template <typename TIn>
+__global__ void __launch_bounds__(kLnWarps * 32)
+row_stats_kernel(const TIn* __restrict__ x, float2* __restrict__ stats, int M, int d, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + warp;
+  if (row >= M) return;
+  const TIn* xr = x + size_t(row) * d;
+  const int nchunks = d >> 3;
+  const float inv_d = 1.0f / float(d);
+  float s = 0.f;
+  for (int c = lane; c < nchunks; c += 32) {
+    float v[8];
+    load8<TIn>(xr + c * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  const float mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+  for (int c = lane; c < nchunks; c += 32) {   // second pass hits L1 (row <= 16 KB)
+    float v[8];
+    load8<TIn>(xr + c * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float t = v[j] - mean; q = fmaf(t, t, q); }
+  }
+  const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+// One-time weight preparation for the folded form of  Linear(LayerNorm(x)):
+//   LN(x) W^T + b = rstd * (x W'^T - mean * colsum) + b',   W' = W * gamma (per input channel, rounded to bf16),
+//   colsum[n] = sum_k W'[n,k] (of the ROUNDED values, so the mean term cancels exactly),  b' = b + W beta.
+template <typename TW>
+__global__ void __launch_bounds__(kLnWarps * 32)
+fold_ln_kernel(const TW* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ w_out, float* __restrict__ colsum,
+               float* __restrict__ bias_out, int N, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kLnWarps + warp;
+  if (n >= N) return;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float wv;
+    if constexpr (sizeof(TW) == 4) wv = w[size_t(n) * K + k];
+    else wv = __bfloat162float(w[size_t(n) * K + k]);
+    const __nv_bfloat16 wf = __float2bfloat16_rn(wv * gamma[k]);
+    w_out[size_t(n) * K + k] = wf;
+    cs += __bfloat162float(wf);
+    bb = fmaf(wv, beta[k], bb);
+  }
+  cs = warp_sum(cs);
+  bb = warp_sum(bb);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_out[n] = bb + (bias ? bias[n] : 0.f);
+  }
+}
+
 template <typename TIn>
 static int launch_ln(const void* x, const float* gamma, const float* beta, void* y, int M, int d, float eps,
                      cudaStream_t s) {
@@ -137,4 +196,48 @@ extern "C" int mt_layernorm(const void* x, int x_dtype, const float* gamma, cons
   if (x_dtype == MT_DT_F32) return launch_ln<float>(x, gamma, beta, y, M, d, eps, s);
   set_error("mt_layernorm: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
   return MT_ERR_BAD_DTYPE;
+}
+
+extern "C" int mt_row_stats(const void* x, int x_dtype, float* stats, int M, int d, float eps, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && stats, MT_ERR_BAD_SHAPE, "mt_row_stats: null pointer");
+  MT_REQUIRE(M > 0 && d > 0 && d % 8 == 0, MT_ERR_BAD_SHAPE, "mt_row_stats: need M > 0 and d %% 8 == 0 (M=%d d=%d)", M, d);
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+             MT_ERR_BAD_ALIGN, "mt_row_stats: x must be 16-byte and stats 8-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = unsigned(ceil_div(M, kLnWarps));
+  if (x_dtype == MT_DT_BF16)
+    row_stats_kernel<__nv_bfloat16><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                   reinterpret_cast<float2*>(stats), M, d, eps);
+  else if (x_dtype == MT_DT_F32)
+    row_stats_kernel<float><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const float*>(x),
+                                                           reinterpret_cast<float2*>(stats), M, d, eps);
+  else {
+    set_error("mt_row_stats: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
+    return MT_ERR_BAD_DTYPE;
+  }
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+extern "C" int mt_fold_layernorm(const void* w, int w_dtype, const float* gamma, const float* beta, const float* bias,
+                                 void* w_folded, float* colsum, float* bias_folded, int N, int K, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(w && gamma && beta && w_folded && colsum && bias_folded, MT_ERR_BAD_SHAPE, "mt_fold_layernorm: null pointer");
+  MT_REQUIRE(N > 0 && K > 0, MT_ERR_BAD_SHAPE, "mt_fold_layernorm: N and K must be positive");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = unsigned(ceil_div(N, kLnWarps));
+  __nv_bfloat16* wo = reinterpret_cast<__nv_bfloat16*>(w_folded);
+  if (w_dtype == MT_DT_F32)
+    fold_ln_kernel<float><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const float*>(w), gamma, beta, bias, wo, colsum,
+                                                         bias_folded, N, K);
+  else if (w_dtype == MT_DT_BF16)
+    fold_ln_kernel<__nv_bfloat16><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(w), gamma, beta,
+                                                                 bias, wo, colsum, bias_folded, N, K);
+  else {
+    set_error("mt_fold_layernorm: w_dtype must be fp32 or bf16 (got %d)", w_dtype);
+    return MT_ERR_BAD_DTYPE;
+  }
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
 }

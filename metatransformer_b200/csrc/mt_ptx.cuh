@@ -76,15 +76,16 @@ MT_DEVINL uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
-#ifndef MT_WAIT_TIMEOUT_CYCLES
-#define MT_WAIT_TIMEOUT_CYCLES (4000000000LL)  // ~2 s at 2 GHz
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.  try_wait itself suspends the
+// thread for a hardware-defined interval, so the loop body is kept to a handful of instructions (spinning role
+// warps share issue slots with the compute warps of their SM sub-partition).
+#ifndef MT_WAIT_MAX_POLLS
+#define MT_WAIT_MAX_POLLS (1u << 24)
 #endif
 MT_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > MT_WAIT_TIMEOUT_CYCLES) {
+    if (++polls > MT_WAIT_MAX_POLLS) {
       printf("[mt_b200] mbarrier wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar,
              parity);
       __trap();

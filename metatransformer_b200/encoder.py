@@ -35,8 +35,9 @@ def build_encoder(scale: str = "base", **overrides) -> nn.Sequential:
 class FusedEncoder(nn.Module):
     """Runs a Sequential of `Block`s through the C-ABI whole-encoder driver (inference / frozen-encoder forward)."""
 
-    def __init__(self, blocks: nn.Sequential):
+    def __init__(self, blocks: nn.Sequential, fold_layernorm: bool = True):
         super().__init__()
+        self.fold_layernorm = fold_layernorm
         if len(blocks) == 0 or not all(isinstance(b, Block) for b in blocks):
             raise TypeError("FusedEncoder needs a non-empty nn.Sequential of metatransformer_b200 Blocks")
         self.blocks = blocks
@@ -50,7 +51,7 @@ class FusedEncoder(nn.Module):
         return tuple((p.data_ptr(), p._version, str(p.device), p.dtype) for p in self.blocks.parameters())
 
     def _ensure_handle(self):
-        key = self._weights_key()
+        key = (self._weights_key(), self.fold_layernorm)
         if self._handle is not None and key == self._handle_key:
             return
         self._destroy()
@@ -73,16 +74,23 @@ class FusedEncoder(nn.Module):
                 return None if t is None else t.data_ptr()
 
             w = arr[i]
-            w.ln1_w = P(blk, "norm1.weight", blk.norm1.weight, torch.float32)
-            w.ln1_b = P(blk, "norm1.bias", blk.norm1.bias, torch.float32)
-            w.qkv_w = P(blk.attn, "qkv.weight", blk.attn.qkv.weight, torch.bfloat16)
-            w.qkv_b = P(blk.attn, "qkv.bias", blk.attn.qkv.bias, torch.float32)
+            if self.fold_layernorm:
+                wq, csq, bq = blk._folded("fold.qkv", blk.attn.qkv, blk.norm1)
+                w1, cs1, b1 = blk._folded("fold.fc1", blk.mlp.fc1, blk.norm2)
+                keep.extend([wq, csq, bq, w1, cs1, b1])
+                w.qkv_w, w.qkv_b, w.qkv_colsum = wq.data_ptr(), bq.data_ptr(), csq.data_ptr()
+                w.fc1_w, w.fc1_b, w.fc1_colsum = w1.data_ptr(), b1.data_ptr(), cs1.data_ptr()
+            else:
+                w.ln1_w = P(blk, "norm1.weight", blk.norm1.weight, torch.float32)
+                w.ln1_b = P(blk, "norm1.bias", blk.norm1.bias, torch.float32)
+                w.qkv_w = P(blk.attn, "qkv.weight", blk.attn.qkv.weight, torch.bfloat16)
+                w.qkv_b = P(blk.attn, "qkv.bias", blk.attn.qkv.bias, torch.float32)
+                w.ln2_w = P(blk, "norm2.weight", blk.norm2.weight, torch.float32)
+                w.ln2_b = P(blk, "norm2.bias", blk.norm2.bias, torch.float32)
+                w.fc1_w = P(blk.mlp, "fc1.weight", blk.mlp.fc1.weight, torch.bfloat16)
+                w.fc1_b = P(blk.mlp, "fc1.bias", blk.mlp.fc1.bias, torch.float32)
             w.proj_w = P(blk.attn, "proj.weight", blk.attn.proj.weight, torch.bfloat16)
             w.proj_b = P(blk.attn, "proj.bias", blk.attn.proj.bias, torch.float32)
-            w.ln2_w = P(blk, "norm2.weight", blk.norm2.weight, torch.float32)
-            w.ln2_b = P(blk, "norm2.bias", blk.norm2.bias, torch.float32)
-            w.fc1_w = P(blk.mlp, "fc1.weight", blk.mlp.fc1.weight, torch.bfloat16)
-            w.fc1_b = P(blk.mlp, "fc1.bias", blk.mlp.fc1.bias, torch.float32)
             w.fc2_w = P(blk.mlp, "fc2.weight", blk.mlp.fc2.weight, torch.bfloat16)
             w.fc2_b = P(blk.mlp, "fc2.bias", blk.mlp.fc2.bias, torch.float32)
         h = ctypes.c_void_p()

@@ -74,6 +74,50 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
+def row_stats(x: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-row LayerNorm statistics of x [M,d] (bf16/fp32): fp32 [M,2] = (mean, rstd)."""
+    _require_cuda(x, out)
+    M, d = x.shape
+    if out is None:
+        out = torch.empty((M, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_row_stats(x.data_ptr(), _DT[x.dtype], out.data_ptr(), M, d, float(eps), _stream()),
+              "mt_row_stats")
+    return out
+
+
+def fold_layernorm(weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor]):
+    """One-time weight preparation for Linear(LayerNorm(x)): returns (W*gamma as bf16 [N,K], colsum [N], b + W beta [N])."""
+    _require_cuda(weight, gamma, beta, bias)
+    if weight.dtype not in (torch.float32, torch.bfloat16):
+        weight = weight.float()
+    N, K = weight.shape
+    wf = torch.empty((N, K), dtype=torch.bfloat16, device=weight.device)
+    cs = torch.empty(N, dtype=torch.float32, device=weight.device)
+    bf = torch.empty(N, dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        check(_lib.load().mt_fold_layernorm(weight.data_ptr(), _DT[weight.dtype], gamma.data_ptr(), beta.data_ptr(),
+                                            _ptr(bias), wf.data_ptr(), cs.data_ptr(), bf.data_ptr(), N, K, _stream()),
+              "mt_fold_layernorm")
+    return wf, cs, bf
+
+
+def linear_ln(x: torch.Tensor, w_folded: torch.Tensor, bias_folded: torch.Tensor, colsum: torch.Tensor,
+              stats: torch.Tensor, gelu: bool = False, cta_group: int = 0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(LayerNorm(x) @ W.T + b) with the LayerNorm folded into the GEMM (see fold_layernorm / row_stats)."""
+    _require_cuda(x, w_folded, bias_folded, colsum, stats, out)
+    M, K = x.shape
+    N = w_folded.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_gemm_bf16_ln(x.data_ptr(), w_folded.data_ptr(), bias_folded.data_ptr(), colsum.data_ptr(),
+                                          stats.data_ptr(), out.data_ptr(), M, N, K, 1 if gelu else 0, cta_group,
+                                          _stream()), "mt_gemm_bf16_ln")
+    return out
+
+
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LayerNorm over the last dim of x [M,d] (bf16 or fp32) -> bf16; weight/bias fp32."""

@@ -177,15 +177,47 @@ class Block(nn.Module):
         _layernorm_eps(self.norm1)
         _layernorm_eps(self.norm2)
 
+    # LayerNorm folding (default): norm1 / norm2 are applied inside the qkv / fc1 GEMM epilogues from per-row
+    # statistics, the normalised activations never touch HBM.  Set to False for the plain LN-kernel + GEMM sequence.
+    fold_layernorm = True
+
+    def _folded(self, name: str, lin: nn.Linear, norm: nn.LayerNorm):
+        """(W*gamma bf16, colsum, b + W beta) for Linear(LayerNorm(.)); cached like `_packed`."""
+        cache = self.__dict__.setdefault("_mt_pack_cache", {})
+        params = (lin.weight, lin.bias, norm.weight, norm.bias)
+        key = tuple(None if q is None else (q.data_ptr(), q._version, q.device, q.dtype) for q in params)
+        hit = cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        w = lin.weight.detach().contiguous()
+        folded = ops.fold_layernorm(w, _packed(self, name + ".g", norm.weight, torch.float32),
+                                    _packed(self, name + ".b", norm.bias, torch.float32),
+                                    _packed(self, name + ".bias", lin.bias, torch.float32))
+        cache[name] = (key, folded)
+        return folded
+
     def _forward_2d(self, x2: torch.Tensor, B: int, N: int) -> torch.Tensor:
-        g1 = _packed(self, "norm1.weight", self.norm1.weight, torch.float32)
-        b1 = _packed(self, "norm1.bias", self.norm1.bias, torch.float32)
-        g2 = _packed(self, "norm2.weight", self.norm2.weight, torch.float32)
-        b2 = _packed(self, "norm2.bias", self.norm2.bias, torch.float32)
-        h = ops.layernorm(x2, g1, b1, self.norm1.eps)
-        x_mid = self.attn._forward_2d(h, B, N, residual=x2)
-        h = ops.layernorm(x_mid, g2, b2, self.norm2.eps, out=h)
-        return self.mlp._forward_2d(h, residual=x_mid)
+        if not self.fold_layernorm:
+            g1 = _packed(self, "norm1.weight", self.norm1.weight, torch.float32)
+            b1 = _packed(self, "norm1.bias", self.norm1.bias, torch.float32)
+            g2 = _packed(self, "norm2.weight", self.norm2.weight, torch.float32)
+            b2 = _packed(self, "norm2.bias", self.norm2.bias, torch.float32)
+            h = ops.layernorm(x2, g1, b1, self.norm1.eps)
+            x_mid = self.attn._forward_2d(h, B, N, residual=x2)
+            h = ops.layernorm(x_mid, g2, b2, self.norm2.eps, out=h)
+            return self.mlp._forward_2d(h, residual=x_mid)
+        attn, mlp = self.attn, self.mlp
+        wq, csq, bq = self._folded("fold.qkv", attn.qkv, self.norm1)
+        stats = ops.row_stats(x2, self.norm1.eps)
+        qkv = ops.linear_ln(x2, wq, bq, csq, stats)
+        o = ops.attention(qkv.view(B, N, -1), attn.num_heads, attn.scale)
+        x_mid = ops.linear(o.view(B * N, -1), _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16),
+                           _packed(attn, "proj.bias", attn.proj.bias, torch.float32), residual=x2)
+        w1, cs1, b1 = self._folded("fold.fc1", mlp.fc1, self.norm2)
+        stats = ops.row_stats(x_mid, self.norm2.eps, out=stats)
+        hid = ops.linear_ln(x_mid, w1, b1, cs1, stats, gelu=True)
+        return ops.linear(hid, _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16),
+                          _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32), residual=x_mid)
 
     def forward(self, x):
         _check_input(x, "Block")

@@ -98,6 +98,26 @@ def test_layernorm_matches_oracle(mt, M, d, dtype):
     _assert_close(y, ref, what=f"layernorm {M}x{d}")
 
 
+@pytest.mark.parametrize("M,N,K,gelu", [(300, 2304, 768, False), (1568, 3072, 768, True), (77, 96, 200, True)])
+def test_layernorm_folded_gemm_matches_oracle(mt, M, N, K, gelu):
+    """Linear(LayerNorm(x)) through mt_fold_layernorm + mt_row_stats + mt_gemm_bf16_ln"""
+    g = torch.Generator().manual_seed(K + N)
+    x = _bf16_round(torch.randn(M, K, generator=g) * 2 + 0.7)          # non-zero mean: exercises the rank-1 term
+    w = torch.randn(N, K, generator=g) * 0.05
+    b = torch.randn(N, generator=g) * 0.5
+    gamma = 1 + torch.randn(K, generator=g) * 0.3
+    beta = torch.randn(K, generator=g) * 0.3
+    ref = orc.linear(orc.layer_norm(x.double(), gamma.double(), beta.double(), 1e-5), w.double(), b.double())
+    if gelu:
+        ref = orc.gelu_erf(ref)
+    wf, cs, bf = mt.ops.fold_layernorm(w.cuda(), gamma.cuda(), beta.cuda(), b.cuda())
+    stats = mt.ops.row_stats(x.cuda().bfloat16(), 1e-5)
+    mean_ref = x.double().mean(-1)
+    assert (stats[:, 0].double().cpu() - mean_ref).abs().max() < 1e-4
+    y = mt.ops.linear_ln(x.cuda().bfloat16(), wf, bf, cs, stats, gelu=gelu)
+    _assert_close(y, ref, what=f"LN-folded gemm {M}x{N}x{K}")
+
+
 @pytest.mark.parametrize("B,N,H", [(1, 1, 1), (2, 17, 2), (1, 128, 1), (2, 196, 3), (1, 256, 2), (1, 257, 1),
                                    (2, 512, 2), (1, 1568, 2)])
 def test_attention_matches_oracle(mt, B, N, H):
@@ -203,6 +223,10 @@ def test_base16_encoder_matches_oracle_c1_shape(mt):
     assert y.dtype == torch.bfloat16
     _assert_close(y, ref, rel=1e-2, mx=3e-2, what="Base-16 x12 fused")
     assert torch.equal(y, y2), "per-Block path and fused driver must launch the same kernels on the same data"
+    # the un-folded sequence (LayerNorm kernel + plain GEMM) must agree with the oracle as well
+    with torch.no_grad():
+        y3 = mt.FusedEncoder(enc, fold_layernorm=False)(x.cuda().bfloat16())
+    _assert_close(y3, ref, rel=1e-2, mx=3e-2, what="Base-16 x12 fused, LayerNorm not folded")
 
 
 def test_full_size_c2_properties(mt):
