@@ -15,7 +15,7 @@
 //   * K/V tiles (128 keys) stream through 3-stage TMA rings shared by both query tiles.
 //
 // Warps (384 threads): 0-3 softmax tile 0, 4-7 softmax tile 1 (warp%4 = TMEM lane quarter), 8 = TMA loader,
-// 9 = MMA issuer + TMEM allocator, 10-11 idle (complete the third warpgroup for setmaxnreg).
+// 9 = S=QK^T issuer + TMEM allocator, 10 = O+=PV issuer, 11 idle (completes the third warpgroup for setmaxnreg).
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 
@@ -145,93 +145,76 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
     }
   } else if (warp == 9) {
-    // =============================== MMA issuer =================================
+    // =============================== S = Q K^T issuer ============================
+    // Two single-thread MMA issuers (this warp and warp 10) instead of one: issuing ~44 tcgen05.mma per work item
+    // from one thread (descriptor arithmetic + barrier polls are a serial dependency chain) was the critical path.
+    // This thread runs ahead on its own, throttled only by s_empty (the softmax warps pulled S_t into registers):
+    // the first score tile of the next work item is computed while the current item is still in its softmax.
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kAtBM, kAtBN, 0, 0);   // S = Q K^T   (both K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(kAtBM, kAtD, 0, 1);    // O = P V     (V is MN-major)
+      constexpr uint32_t idesc_s = make_idesc_bf16(kAtBM, kAtBN, 0, 0);   // both operands K-major
       int kst = 0; uint32_t kph = 0;
-      int vst = 0; uint32_t vph = 0;
-      uint32_t n_s[kAtQT] = {0, 0};  // S_t tiles issued so far
-      uint32_t n_p[kAtQT] = {0, 0};  // P_t tiles consumed so far
+      uint32_t n_s0 = 0, n_s1 = 0;   // S_t tiles issued so far
       uint32_t it = 0;
-
-      auto issue_s = [&](int t, int qb, int kstage) {
-        // wait until the softmax warps pulled the previous S_t out of TMEM
-        mbar_wait(s_empty(t), (n_s[t] & 1u) ^ 1u);
-        tc_fence_after();
-        const uint64_t adesc = make_smem_desc_sw128(q_smem(qb, t));
-        const uint64_t bdesc = make_smem_desc_sw128(smem_base + kAtSmemK + kstage * kAtTileBytes);
-#pragma unroll
-        for (int k = 0; k < kAtD / 16; ++k)
-          umma_f16_ss<1>(tmem_base + kAtTmemS + t * kAtBN, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s,
-                         k > 0 ? 1u : 0u);
-        umma_commit(s_full(t));
-        ++n_s[t];
-      };
-
-      // Issue order per KV step: next S0, next S1, P0·V, P1·V — where "next S" is the following KV tile of this item
-      // or, on the last tile, the FIRST tile of the next work item (its Q sits in the other Q buffer), so the softmax
-      // warps never wait for a cold pipeline between items.
-      bool first = true;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int qb = int(it & 1u);
-        const bool has_next_item = (item + int(gridDim.x) < p.num_items);
-        if (first) {
-          first = false;
+        for (int j = 0; j < p.num_kv; ++j) {
           mbar_wait(k_full(kst), kph);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_base + kAtSmemK + kst * kAtTileBytes);
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
-            mbar_wait(q_full(qb, t), (it >> 1) & 1u);
+            if (j == 0) mbar_wait(q_full(qb, t), (it >> 1) & 1u);
+            uint32_t& n_s = (t == 0) ? n_s0 : n_s1;
+            mbar_wait(s_empty(t), (n_s & 1u) ^ 1u);
+            ++n_s;
             tc_fence_after();
-            issue_s(t, qb, kst);
-            if (p.num_kv == 1) umma_commit(q_empty(qb, t));
+            const uint64_t adesc = make_smem_desc_sw128(q_smem(qb, t));
+            const uint32_t d_tmem = tmem_base + kAtTmemS + t * kAtBN;
+            umma_f16_ss<1>(d_tmem, adesc, bdesc, idesc_s, 0u);
+            umma_f16_ss<1>(d_tmem, adesc + 2u, bdesc + 2u, idesc_s, 1u);
+            umma_f16_ss<1>(d_tmem, adesc + 4u, bdesc + 4u, idesc_s, 1u);
+            umma_f16_ss<1>(d_tmem, adesc + 6u, bdesc + 6u, idesc_s, 1u);
+            umma_commit(s_full(t));
+            if (j + 1 == p.num_kv) umma_commit(q_empty(qb, t));   // last use of Q_t for this item
           }
           umma_commit(k_empty(kst));
           if (++kst == kAtStages) { kst = 0; kph ^= 1u; }
         }
+      }
+    }
+  } else if (warp == 10) {
+    // =============================== O += P V issuer =============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = make_idesc_bf16(kAtBM, kAtD, 0, 1);    // V is consumed MN-major
+      int vst = 0; uint32_t vph = 0;
+      uint32_t n_p0 = 0, n_p1 = 0;   // P_t tiles consumed so far
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         for (int j = 0; j < p.num_kv; ++j) {
           const int valid = min(kAtBN, p.N - j * kAtBN);
           const int ksteps = 2 * ((valid + 31) / 32);  // 16-key steps covering the valid 32-key chunks
-          const bool more = (j + 1 < p.num_kv);
-          const bool next_s = more || has_next_item;
           mbar_wait(v_full(vst), vph);
-          if (next_s) mbar_wait(k_full(kst), kph);
-          // ---- next S_t first: it only needs the softmax warps to have pulled S_t(j) into registers, so the tensor
-          //      core produces the next scores while the softmax warps are still exponentiating the current ones ----
-          if (next_s) {
-#pragma unroll
-            for (int t = 0; t < kAtQT; ++t) {
-              if (more) {
-                issue_s(t, qb, kst);
-                if (j + 2 == p.num_kv) umma_commit(q_empty(qb, t));  // last use of Q_t for this item
-              } else {
-                const uint32_t nit = it + 1;
-                mbar_wait(q_full(int(nit & 1u), t), (nit >> 1) & 1u);
-                tc_fence_after();
-                issue_s(t, int(nit & 1u), kst);
-                if (p.num_kv == 1) umma_commit(q_empty(int(nit & 1u), t));
-              }
-            }
-            umma_commit(k_empty(kst));
-          }
+          const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + kAtSmemV + vst * kAtTileBytes);
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
-            // ---- O_t (+)= P_t(j) V_j ----
-            mbar_wait(p_full(t), n_p[t] & 1u);
-            ++n_p[t];
+            uint32_t& n_p = (t == 0) ? n_p0 : n_p1;
+            mbar_wait(p_full(t), n_p & 1u);
+            ++n_p;
             tc_fence_after();
-            const uint32_t pbase = smem_base + kAtSmemP + t * 2 * kAtTileBytes;
-            const uint32_t vbase = smem_base + kAtSmemV + vst * kAtTileBytes;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = make_smem_desc_sw128(pbase + (k >> 2) * kAtTileBytes) + uint64_t(2 * (k & 3));
-              const uint64_t bdesc = make_smem_desc_sw128(vbase + k * 16 * 128);  // 16 keys = 16 rows of 128 B
-              umma_f16_ss<1>(tmem_base + kAtTmemO + t * kAtD, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            const uint64_t adesc0 = make_smem_desc_sw128(smem_base + kAtSmemP + t * 2 * kAtTileBytes);
+            const uint32_t d_tmem = tmem_base + kAtTmemO + t * kAtD;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (k < ksteps) {
+                // A: P chunk (k / 4) is 16 KB further, 32 B per 16-key step inside a 128 B row;
+                // B: 16 keys = 16 rows of 128 B = 2 KB per step (descriptor address field is in 16-byte units)
+                const uint64_t adesc = adesc0 + uint64_t((k >> 2) * (kAtTileBytes >> 4) + 2 * (k & 3));
+                const uint64_t bdesc = bdesc0 + uint64_t(k * (16 * 128 >> 4));
+                umma_f16_ss<1>(d_tmem, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+              }
             }
             umma_commit(o_done(t));
-            if (t == kAtQT - 1) umma_commit(v_empty(vst));
           }
+          umma_commit(v_empty(vst));
           if (++vst == kAtStages) { vst = 0; vph ^= 1u; }
-          if (next_s) { if (++kst == kAtStages) { kst = 0; kph ^= 1u; } }
         }
       }
     }

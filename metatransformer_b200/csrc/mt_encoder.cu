@@ -88,8 +88,8 @@ extern "C" int mt_encoder_forward(mt_encoder* enc, const void* x, void* y, int B
   const WsLayout w = ws_layout(enc, size_t(M));
   MT_REQUIRE(workspace_bytes >= w.total, MT_ERR_BAD_SHAPE, "mt_encoder_forward: workspace too small (%zu < %zu)",
              workspace_bytes, w.total);
-  MT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, MT_ERR_BAD_ALIGN,
-             "mt_encoder_forward: workspace must be 1024-byte aligned");
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, MT_ERR_BAD_ALIGN,
+             "mt_encoder_forward: workspace must be 256-byte aligned");
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   void* h = ws + w.h;
   void* qkv = ws + w.qkv;

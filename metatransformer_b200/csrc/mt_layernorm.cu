@@ -109,32 +109,60 @@ layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma, con
 
 // Row statistics only: stats[row] = (mean, rstd).  Feeds the LN-folded GEMM epilogue (mt_gemm_bf16_ln), which
 // makes the normalised activations never touch HBM.  Algorithmic traffic: M*d*sizeof(in) + 8*M bytes.
-template <typename TIn>
+template <int NV, typename TIn>
 __global__ void __launch_bounds__(kLnWarps * 32)
 row_stats_kernel(const TIn* __restrict__ x, float2* __restrict__ stats, int M, int d, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + warp;
   if (row >= M) return;
   const TIn* xr = x + size_t(row) * d;
-  const int nchunks = d >> 3;
   const float inv_d = 1.0f / float(d);
-  float s = 0.f;
-  for (int c = lane; c < nchunks; c += 32) {
-    float v[8];
-    load8<TIn>(xr + c * 8, v);
+  float mean, q = 0.f;
+  if constexpr (NV > 0) {
+    // d == NV*256: all of the row's 16-byte loads are issued up front and the row stays in registers
+    float v[NV][8];
+    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += v[j];
-  }
-  const float mean = warp_sum(s) * inv_d;
-  float q = 0.f;
-  for (int c = lane; c < nchunks; c += 32) {   // second pass hits L1 (row <= 16 KB)
-    float v[8];
-    load8<TIn>(xr + c * 8, v);
+    for (int i = 0; i < NV; ++i) load8<TIn>(xr + (lane + 32 * i) * 8, v[i]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float t = v[j] - mean; q = fmaf(t, t, q); }
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    mean = warp_sum(s) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; q = fmaf(t, t, q); }
+  } else {
+    const int nchunks = d >> 3;
+    float s = 0.f;
+    for (int c = lane; c < nchunks; c += 32) {
+      float v[8];
+      load8<TIn>(xr + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    mean = warp_sum(s) * inv_d;
+    for (int c = lane; c < nchunks; c += 32) {   // second pass hits L1 (row <= 16 KB)
+      float v[8];
+      load8<TIn>(xr + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float t = v[j] - mean; q = fmaf(t, t, q); }
+    }
   }
   const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
   if (lane == 0) stats[row] = make_float2(mean, rstd);
+}
+
+template <typename TIn>
+static void launch_row_stats(const void* x, float* stats, int M, int d, float eps, cudaStream_t s) {
+  const TIn* xp = reinterpret_cast<const TIn*>(x);
+  float2* sp = reinterpret_cast<float2*>(stats);
+  const unsigned grid = unsigned(ceil_div(M, kLnWarps));
+  const unsigned block = kLnWarps * 32;
+  if (d == 768) row_stats_kernel<3, TIn><<<grid, block, 0, s>>>(xp, sp, M, d, eps);
+  else if (d == 1024) row_stats_kernel<4, TIn><<<grid, block, 0, s>>>(xp, sp, M, d, eps);
+  else row_stats_kernel<0, TIn><<<grid, block, 0, s>>>(xp, sp, M, d, eps);
 }
 
 // One-time weight preparation for the folded form of  Linear(LayerNorm(x)):
@@ -205,13 +233,8 @@ extern "C" int mt_row_stats(const void* x, int x_dtype, float* stats, int M, int
   MT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
              MT_ERR_BAD_ALIGN, "mt_row_stats: x must be 16-byte and stats 8-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const unsigned grid = unsigned(ceil_div(M, kLnWarps));
-  if (x_dtype == MT_DT_BF16)
-    row_stats_kernel<__nv_bfloat16><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                                   reinterpret_cast<float2*>(stats), M, d, eps);
-  else if (x_dtype == MT_DT_F32)
-    row_stats_kernel<float><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const float*>(x),
-                                                           reinterpret_cast<float2*>(stats), M, d, eps);
+  if (x_dtype == MT_DT_BF16) launch_row_stats<__nv_bfloat16>(x, stats, M, d, eps, s);
+  else if (x_dtype == MT_DT_F32) launch_row_stats<float>(x, stats, M, d, eps, s);
   else {
     set_error("mt_row_stats: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
     return MT_ERR_BAD_DTYPE;

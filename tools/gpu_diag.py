@@ -210,14 +210,29 @@ def group_prof():
     torch.cuda.synchronize()
 
 
-GROUPS = {"prof": group_prof, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+def group_prof_fc1():
+    """fc1-shaped GEMM (K=768, N=3072, GELU epilogue), cg=2, for an ncu capture of the epilogue-heavy case"""
+    import torch
+    from metatransformer_b200 import ops
+    dev = "cuda"
+    M, N, K = 50176, 3072, 768
+    x = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    b = torch.randn(N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.linear(x, w, b, None, gelu=True, cta_group=2, out=out)
+    torch.cuda.synchronize()
+
+
+GROUPS = {"prof": group_prof, "prof_fc1": group_prof_fc1, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
 
 
 def main():
     if len(sys.argv) > 1 and sys.argv[1] in GROUPS:
         GROUPS[sys.argv[1]]()
         return
-    names = sys.argv[1:] if len(sys.argv) > 1 else [g for g in GROUPS if g != "prof"]
+    names = sys.argv[1:] if len(sys.argv) > 1 else [g for g in GROUPS if not g.startswith("prof")]
     outdir = ROOT / "gpurun_out" / "diag"
     outdir.mkdir(parents=True, exist_ok=True)
     for name in names:
