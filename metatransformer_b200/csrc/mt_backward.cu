@@ -1,0 +1,132 @@
+// mt_backward.cu — element-wise / row-wise backward pieces of the Block (the tokenizers are
+// trainable under a frozen encoder, Audio/src/models/ast_models.py:66-70, so dX must flow through every Block).
+//   * mt_layernorm_bwd: dx = add + rstd * (g - mean_d(g) - xhat * mean_d(g * xhat)),  g = dy * gamma, xhat = (x-mean)*rstd
+//   * mt_gelu:          h = gelu(u) (training-mode forward keeps the pre-activation u for the backward pass)
+// Both are HBM-bound streaming kernels: one warp per row / 16-byte vectors.
+#include "mt_ptx.cuh"
+#include "mt_common.cuh"
+
+namespace mt {
+
+constexpr int kBwWarps = 8;
+
+MT_DEVINL void ld8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+  v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+}
+MT_DEVINL float warp_sum_bw(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// generic d (d % 8 == 0): the row is re-read for the second pass (L1/L2 hits; rows are <= 16 KB)
+__global__ void __launch_bounds__(kBwWarps * 32)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const float2* __restrict__ stats, const float* __restrict__ gamma,
+                     const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx, int M, int d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kBwWarps + warp;
+  if (row >= M) return;
+  const size_t base = size_t(row) * d;
+  const float2 st = stats[row];
+  const float mean = st.x, rstd = st.y;
+  const int nchunks = d >> 3;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < nchunks; c += 32) {
+    float g[8], xv[8];
+    ld8_bf16(dy + base + c * 8, g);
+    ld8_bf16(x + base + c * 8, xv);
+    if (gamma != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= gamma[c * 8 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1 += g[j];
+      s2 = fmaf(g[j], (xv[j] - mean) * rstd, s2);
+    }
+  }
+  const float inv_d = 1.0f / float(d);
+  const float m1 = warp_sum_bw(s1) * inv_d, m2 = warp_sum_bw(s2) * inv_d;
+  for (int c = lane; c < nchunks; c += 32) {
+    float g[8], xv[8], a[8];
+    ld8_bf16(dy + base + c * 8, g);
+    ld8_bf16(x + base + c * 8, xv);
+    if (add != nullptr) ld8_bf16(add + base + c * 8, a);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float gj = g[j];
+      if (gamma != nullptr) gj *= gamma[c * 8 + j];
+      const float xh = (xv[j] - mean) * rstd;
+      o[j] = rstd * (gj - m1 - xh * m2) + (add != nullptr ? a[j] : 0.f);
+    }
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(dx + base + c * 8) = w;
+  }
+}
+
+MT_DEVINL float gelu_erf_ref(float x) {
+  const float t = fminf(fabsf(x), 12.0f);
+  float p = -0.00048811757005751133f;
+  p = fmaf(p, t, 0.007198806386440992f);
+  p = fmaf(p, t, -0.052146803587675095f);
+  p = fmaf(p, t, -0.4595957100391388f);
+  p = fmaf(p, t, -1.1510006189346313f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * t));
+  return fmaf(t * e, -0.5f, fmaxf(x, 0.0f));
+}
+
+__global__ void __launch_bounds__(256) gelu_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ h,
+                                                    size_t n8) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    ld8_bf16(u + i * 8, v);
+    uint4 w;
+    w.x = pack_bf16x2(gelu_erf_ref(v[0]), gelu_erf_ref(v[1])); w.y = pack_bf16x2(gelu_erf_ref(v[2]), gelu_erf_ref(v[3]));
+    w.z = pack_bf16x2(gelu_erf_ref(v[4]), gelu_erf_ref(v[5])); w.w = pack_bf16x2(gelu_erf_ref(v[6]), gelu_erf_ref(v[7]));
+    *reinterpret_cast<uint4*>(h + i * 8) = w;
+  }
+}
+
+}  // namespace mt
+
+extern "C" int mt_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const void* add,
+                                void* dx, int M, int d, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(dy && x && stats && dx, MT_ERR_BAD_SHAPE, "mt_layernorm_bwd: null pointer");
+  MT_REQUIRE(M > 0 && d > 0 && d % 8 == 0, MT_ERR_BAD_SHAPE, "mt_layernorm_bwd: need M > 0 and d %% 8 == 0");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+               reinterpret_cast<uintptr_t>(add)) & 15) == 0, MT_ERR_BAD_ALIGN,
+             "mt_layernorm_bwd: tensors must be 16-byte aligned");
+  layernorm_bwd_kernel<<<unsigned(ceil_div(M, kBwWarps)), kBwWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
+      reinterpret_cast<const float2*>(stats), gamma, reinterpret_cast<const __nv_bfloat16*>(add),
+      reinterpret_cast<__nv_bfloat16*>(dx), M, d);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+extern "C" int mt_gelu(const void* u, void* h, size_t n, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(u && h, MT_ERR_BAD_SHAPE, "mt_gelu: null pointer");
+  MT_REQUIRE(n % 8 == 0, MT_ERR_BAD_SHAPE, "mt_gelu: n must be a multiple of 8");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(h)) & 15) == 0, MT_ERR_BAD_ALIGN,
+             "mt_gelu: tensors must be 16-byte aligned");
+  if (n == 0) return MT_OK;
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > size_t(sms) * 16) blocks = size_t(sms) * 16;
+  gelu_kernel<<<unsigned(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(u), reinterpret_cast<__nv_bfloat16*>(h), n / 8);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}

@@ -54,7 +54,7 @@ struct GemmParams {
   const __nv_bfloat16* resid;   // [M, ldr] bf16 or nullptr
   int ldr;
   int M, N, K;
-  int act;                      // 0 = identity, 1 = exact-erf GELU
+  int act;                      // 0 = identity, 1 = exact-erf GELU, 2 = multiply by gelu'(resid) (backward)
   int num_m_tiles, num_n_tiles;
   // LayerNorm folded into the GEMM (see mt_fold_layernorm): y = rstd_m * (acc - mean_m * colsum_n) + bias_n
   const float2* row_stats;      // [M] (mean, rstd) or nullptr
@@ -74,6 +74,40 @@ MT_DEVINL float gelu_erf(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * t));
   return fmaf(t * e, -0.5f, fmaxf(x, 0.0f));
+}
+
+// d/dx gelu(x) = Phi(x) + x*phi(x), same erfc fit as gelu_erf (backward of the MLP activation)
+MT_DEVINL float gelu_erf_grad(float x) {
+  const float t = fminf(fabsf(x), 12.0f);
+  float p = -0.00048811757005751133f;
+  p = fmaf(p, t, 0.007198806386440992f);
+  p = fmaf(p, t, -0.052146803587675095f);
+  p = fmaf(p, t, -0.4595957100391388f);
+  p = fmaf(p, t, -1.1510006189346313f);
+  float e, g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * t));                      // erfc(|x|/sqrt2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(t * t * -0.7213475204444817f)); // exp(-x^2/2)
+  const float cdf = (x >= 0.f) ? fmaf(e, -0.5f, 1.0f) : 0.5f * e;
+  return fmaf(x * 0.3989422804014327f, g, cdf);
+}
+
+// two elements at a time with packed fp32x2 FMAs (the epilogue is issue-bound: ~1/3 fewer instruction slots)
+MT_DEVINL uint64_t gelu_erf_x2(uint64_t x) {
+  float x0, x1;
+  unpack_f32x2(x, x0, x1);
+  const uint64_t t = pack_f32x2(fminf(fabsf(x0), 12.0f), fminf(fabsf(x1), 12.0f));
+  uint64_t p = pack_f32x2(-0.00048811757005751133f, -0.00048811757005751133f);
+  p = fma_f32x2(p, t, pack_f32x2(0.007198806386440992f, 0.007198806386440992f));
+  p = fma_f32x2(p, t, pack_f32x2(-0.052146803587675095f, -0.052146803587675095f));
+  p = fma_f32x2(p, t, pack_f32x2(-0.4595957100391388f, -0.4595957100391388f));
+  p = fma_f32x2(p, t, pack_f32x2(-1.1510006189346313f, -1.1510006189346313f));
+  float w0, w1;
+  unpack_f32x2(mul_f32x2(p, t), w0, w1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w1));
+  const uint64_t te = mul_f32x2(t, pack_f32x2(e0, e1));
+  return fma_f32x2(te, pack_f32x2(-0.5f, -0.5f), pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
 }
 
 template <int CG>
@@ -223,6 +257,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           ln_nmr = -st.x * st.y;
         }
       }
+      const uint64_t ln_rstd2 = pack_f32x2(ln_rstd, ln_rstd), ln_nmr2 = pack_f32x2(ln_nmr, ln_nmr);
       // residual slices are fetched one 32-column slice ahead of their use (the first one before the accumulator
       // is even ready), so the L2/HBM latency hides behind the MMAs of this tile and the math of the previous slice
       const bool row_ok = (p.resid != nullptr) && (row < p.M);
@@ -274,17 +309,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const float4 b4 = reinterpret_cast<const float4*>(bias_s)[8 * sc + j];
           const float4 c4 = reinterpret_cast<const float4*>(bias_s)[32 + 8 * sc + j];
           // rstd*(acc - mean*colsum) + bias; without LN folding rstd = 1 and colsum = 0: plain acc + bias
-          float v0 = fmaf(__uint_as_float(acc[4 * j + 0]), ln_rstd, fmaf(ln_nmr, c4.x, b4.x));
-          float v1 = fmaf(__uint_as_float(acc[4 * j + 1]), ln_rstd, fmaf(ln_nmr, c4.y, b4.y));
-          float v2 = fmaf(__uint_as_float(acc[4 * j + 2]), ln_rstd, fmaf(ln_nmr, c4.z, b4.z));
-          float v3 = fmaf(__uint_as_float(acc[4 * j + 3]), ln_rstd, fmaf(ln_nmr, c4.w, b4.w));
+          uint64_t v01 = fma_f32x2(pack_f32x2(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1])), ln_rstd2,
+                                   fma_f32x2(ln_nmr2, pack_f32x2(c4.x, c4.y), pack_f32x2(b4.x, b4.y)));
+          uint64_t v23 = fma_f32x2(pack_f32x2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])), ln_rstd2,
+                                   fma_f32x2(ln_nmr2, pack_f32x2(c4.z, c4.w), pack_f32x2(b4.z, b4.w)));
           if (p.act == 1) {
-            v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+            v01 = gelu_erf_x2(v01);
+            v23 = gelu_erf_x2(v23);
           }
           const uint32_t r01 = (j & 1) ? rv[j >> 1].z : rv[j >> 1].x;  // columns 4j, 4j+1
           const uint32_t r23 = (j & 1) ? rv[j >> 1].w : rv[j >> 1].y;  // columns 4j+2, 4j+3
-          v0 += bf16_lo(r01); v1 += bf16_hi(r01);
-          v2 += bf16_lo(r23); v3 += bf16_hi(r23);
+          if (p.act == 2) {
+            // backward of fc1's GELU: the "residual" operand holds the saved pre-activation u; y = acc * gelu'(u)
+            v01 = mul_f32x2(v01, pack_f32x2(gelu_erf_grad(bf16_lo(r01)), gelu_erf_grad(bf16_hi(r01))));
+            v23 = mul_f32x2(v23, pack_f32x2(gelu_erf_grad(bf16_lo(r23)), gelu_erf_grad(bf16_hi(r23))));
+          } else {
+            v01 = add_f32x2(v01, pack_f32x2(bf16_lo(r01), bf16_hi(r01)));
+            v23 = add_f32x2(v23, pack_f32x2(bf16_lo(r23), bf16_hi(r23)));
+          }
+          float v0, v1, v2, v3;
+          unpack_f32x2(v01, v0, v1);
+          unpack_f32x2(v23, v2, v3);
           packed[2 * j + 0] = pack_bf16x2(v0, v1);
           packed[2 * j + 1] = pack_bf16x2(v2, v3);
         }
@@ -406,7 +451,9 @@ static int gemm_entry(const char* who, const void* x, const void* w, const float
                  (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(colsum) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(row_stats) & 7) == 0,
              MT_ERR_BAD_ALIGN, "%s: all pointers must be 16-byte aligned", who);
-  MT_REQUIRE(act == 0 || act == 1, MT_ERR_UNSUPPORTED, "%s: act must be 0 (none) or 1 (gelu)", who);
+  MT_REQUIRE(act == 0 || act == 1 || act == 2, MT_ERR_UNSUPPORTED,
+             "%s: act must be 0 (none), 1 (gelu) or 2 (times gelu'(residual))", who);
+  MT_REQUIRE(act != 2 || residual != nullptr, MT_ERR_BAD_SHAPE, "%s: act 2 needs the pre-activation as `residual`", who);
   MT_REQUIRE((row_stats == nullptr) == (colsum == nullptr), MT_ERR_BAD_SHAPE,
              "%s: row_stats and colsum must be given together", who);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
