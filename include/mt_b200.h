@@ -40,7 +40,7 @@ int mt_device_ok(int device);         /* 0 if `device` is compute capability 10.
 
 /* ---- E3/E5/E6: Linear (+bias) (+GELU) (+residual)  --------------------------------------------------------
  * y[M,N] = act(x[M,K] @ w[N,K]^T + bias[N]) (+ residual[M,N]);  x,w,residual,y bf16; bias fp32 (may be NULL).
- * act: 0 = identity, 1 = exact-erf GELU (nn.GELU()).  cta_group: 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs.
+ * act: 0 = identity, 1 = exact-erf GELU (nn.GELU()), 2 = y = acc * gelu'(residual) (backward).  cta_group: 0 = auto, 1 = single-CTA tiles, 2 = CTA pairs.
  * Replaces F.linear at PointCloud/openpoints/models/layers/attention.py:28 (qkv), :36 (proj) and
  * mlp.py:30-33 (fc1, act, fc2), plus the residual adds of Block.forward (attention.py:56-57).           */
 int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y,
@@ -65,11 +65,33 @@ int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float* bias_folde
 int mt_layernorm(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
                  int M, int d, float eps, void* stream);
 
+/* ---- E8 (backward pieces) -----------------------------------------------------------------------------------
+ * mt_layernorm_bwd: dx = add + rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma (gamma NULL = already folded),
+ *                   xhat = (x - mean)*rstd with (mean, rstd) from mt_row_stats; dy, x, add, dx bf16 [M,d].
+ * mt_gelu:          h = gelu(u), bf16, n % 8 == 0 (training-mode forward keeps u for mt_gemm_bf16 act = 2).
+ * Autograd of Block.forward (attention.py:55-58) when only the tokenizer trains (Audio/src/models/ast_models.py:66-70). */
+int mt_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const void* add, void* dx,
+                     int M, int d, void* stream);
+int mt_gelu(const void* u, void* h, size_t n, void* stream);
+/* weight-gradient helpers for the trainable tokenizers: dW = dY^T X is run as the TN GEMM on transposed copies
+ * (mt_transpose_bf16: dst[C, ldd] = src[R, C]^T, zero-padded to ldd >= R), db = column sums of dY (fp32).  */
+int mt_transpose_bf16(const void* src, void* dst, int R, int C, int ldd, void* stream);
+int mt_colsum(const void* x, float* out, int M, int N, void* stream);
+
 /* ---- E4: softmax attention core -----------------------------------------------------------------------------
  * qkv: bf16 [B, N, 3, H, dh] (the packed output of the qkv Linear, attention.py:28), out: bf16 [B, N, H*dh].
  * out[b,n,h,:] = softmax_j(scale * q[b,n,h]·k[b,j,h]) · v[b,j,h]   (attention.py:31-35, no mask, no dropout).
  * dh must be 64.                                                                                             */
 int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
+
+/* Same, additionally writing lse2[B,H,N] = log2-sum-exp of the scaled scores (needed by mt_attention_bwd). */
+int mt_attention_fwd_lse(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale,
+                         void* stream);
+/* Backward of the attention core (E8): dqkv [B,N,3,H,64] bf16 from qkv, out, d(out) and the forward's lse2.
+ * workspace: mt_attention_bwd_workspace_bytes (fp32 dQ accumulator + row-wise delta = sum(dout*out)).       */
+int mt_attention_bwd_workspace_bytes(int B, int N, int H, size_t* bytes);
+int mt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                     void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale, void* stream);
 
 /* ---- T1/T2/T3: patch / spectrogram / tubelet embedding -----------------------------------------------------
  * Non-overlapping or strided Conv{2,3}d as im2row + GEMM.

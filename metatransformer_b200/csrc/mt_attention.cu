@@ -54,6 +54,7 @@ struct AttnParams {
   int num_kv;        // ceil(N / 128)
   int num_items;     // B * H * num_qp
   float scale_log2;  // scale * log2(e)
+  float* lse2;       // optional [B, H, N]: log2-sum-exp of the scaled scores (m*c + log2 l), saved for the backward
 };
 
 __global__ void __launch_bounds__(kAtThreads, 1)
@@ -107,6 +108,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int H = p.H;
 
@@ -362,6 +365,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       ++n_od;
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
+      {
+        const int qrow = qp * 256 + t * 128 + r_in_tile;
+        if (p.lse2 != nullptr && qrow < p.N) p.lse2[(size_t(b) * H + h) * p.N + qrow] = fmaf(m_run, c, log2f(l_run));
+      }
       uint32_t ob[32];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -401,7 +408,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
 }  // namespace mt
 
-extern "C" int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream) {
+static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale,
+                              void* stream) {
   using namespace mt;
   MT_REQUIRE(qkv && out, MT_ERR_BAD_SHAPE, "mt_attention_fwd: null pointer");
   MT_REQUIRE(B > 0 && N > 0 && H > 0, MT_ERR_BAD_SHAPE, "mt_attention_fwd: B, N, H must be positive");
@@ -434,6 +442,7 @@ extern "C" int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H,
   p.num_kv = ceil_div(N, kAtBN);
   p.num_items = B * H * p.num_qp;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse2 = lse2;
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
@@ -443,8 +452,20 @@ extern "C" int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H,
     MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
     attr_set = true;
   }
-  attention_fwd_kernel<<<unsigned(grid), kAtThreads, kAtSmemBytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm_qkv, tm_out,
-                                                                                                            p);
-  MT_CHECK_CUDA(cudaGetLastError());
+  MT_CHECK_CUDA(launch_pdl(attention_fwd_kernel, dim3(unsigned(grid)), dim3(kAtThreads), size_t(kAtSmemBytes),
+                           reinterpret_cast<cudaStream_t>(stream), 1u, tm_qkv, tm_out, p));
   return MT_OK;
+}
+
+extern "C" int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream) {
+  return attention_fwd_impl(qkv, out, nullptr, B, N, H, dh, scale, stream);
+}
+
+extern "C" int mt_attention_fwd_lse(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale,
+                                    void* stream) {
+  if (!lse2) {
+    mt::set_error("mt_attention_fwd_lse: lse2 is required");
+    return MT_ERR_BAD_SHAPE;
+  }
+  return attention_fwd_impl(qkv, out, lse2, B, N, H, dh, scale, stream);
 }

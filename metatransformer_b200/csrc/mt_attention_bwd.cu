@@ -1,0 +1,410 @@
+// mt_attention_bwd.cu — backward of the softmax attention core (SURVEY.md §8a rows E4 + E8): gradients of
+//   O = softmax(Q K^T * scale) V        (PointCloud/openpoints/models/layers/attention.py:31-35)
+// with respect to q, k, v, written in the packed (B, N, 3, H, 64) layout of the qkv Linear's output so that the
+// dgrad GEMM of `attn.qkv` can consume it directly.  Needed because the tokenizers train under a frozen encoder
+// (Audio/src/models/ast_models.py:66-70): dX must flow through every Block.
+//
+// FlashAttention-2-style recomputation, Blackwell edition (sm_100a only, head_dim 64):
+//   work item = (batch, head, key tile j of 128 keys); loop over query tiles i of 128 rows:
+//     S^T  = K_j Q_i^T            tcgen05.mma 128x128x16   (TMEM cols   0..127)
+//     dP^T = V_j dO_i^T           tcgen05.mma 128x128x16   (TMEM cols 128..255)
+//     P^T  = exp2(S^T c - lse2_i) ;  dS^T = P^T (dP^T - delta_i) scale      (one key row per thread, fp32 registers)
+//     dV_j += P^T  dO_i           A = P^T  (smem, K-major),  B = dO_i (MN-major)     (TMEM cols 256..319)
+//     dK_j += dS^T Q_i            A = dS^T (smem, K-major),  B = Q_i  (MN-major)     (TMEM cols 320..383)
+//     dQ_i  = dS   K_j            A = dS^T read MN-major,     B = K_j  (MN-major)     (TMEM cols 384..447)
+//   dQ_i partials are added to an fp32 accumulator in HBM (red.global.add), dK_j / dV_j leave once per item.
+//   lse2 = log2-sum-exp saved by the forward, delta_i = rowsum(dO_i * O_i) from a small pre-pass kernel.
+// Warps: 0-3 compute (warp = TMEM lane quarter), 4 = TMA loader, 5 = MMA issuer + TMEM allocator.
+#include "mt_ptx.cuh"
+#include "mt_common.cuh"
+
+namespace mt {
+
+constexpr int kAbT = 128 * 64 * 2;          // bytes of one 128 x 64 bf16 tile
+constexpr int kAbSmemK = 0;
+constexpr int kAbSmemV = kAbSmemK + kAbT;
+constexpr int kAbSmemQ = kAbSmemV + kAbT;   // 2 stages
+constexpr int kAbSmemDO = kAbSmemQ + 2 * kAbT;
+constexpr int kAbSmemP = kAbSmemDO + 2 * kAbT;   // P^T: 2 chunks of 64 queries
+constexpr int kAbSmemDS = kAbSmemP + 2 * kAbT;   // dS^T
+constexpr int kAbSmemStat = kAbSmemDS + 2 * kAbT;  // 2 x (128 lse2 + 128 delta) floats
+constexpr int kAbSmemBar = kAbSmemStat + 2 * 256 * 4;
+// barriers: kv_full kv_empty qd_full[2] qd_empty[2] s_full s_empty p_full pv_done dq_empty kvacc_full kvacc_empty
+constexpr int kAbNumBars = 13;
+constexpr int kAbSmemTmemPtr = kAbSmemBar + kAbNumBars * 8;
+constexpr int kAbSmemBytes = kAbSmemTmemPtr + 16 + 1024;
+constexpr int kAbThreads = 192;
+constexpr uint32_t kAbTmS = 0, kAbTmDP = 128, kAbTmDV = 256, kAbTmDK = 320, kAbTmDQ = 384;
+
+struct AttnBwdParams {
+  int B, N, H;
+  int num_t;         // ceil(N / 128): key tiles == query tiles
+  int num_items;     // B * H * num_t
+  float scale, scale_log2;
+  const float* lse2;     // [B, H, N]
+  const float* delta;    // [B, H, N]
+  float* dq_acc;         // [B, N, H, 64] fp32, zero-initialised
+  __nv_bfloat16* dqkv;   // [B, N, 3, H, 64]
+};
+
+MT_DEVINL float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]   (one warp per (b,n) row; lane pairs cover one head)
+__global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                              const __nv_bfloat16* __restrict__ dout,
+                                                              float* __restrict__ delta, int B, int N, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;   // b*N + n
+  if (row >= (long long)B * N) return;
+  const int b = int(row / N), n = int(row % N);
+  const size_t base = size_t(row) * H * 64;
+  for (int c0 = 0; c0 < H * 8; c0 += 32) {   // 8-element chunks; 8 chunks per head; all lanes stay in the loop
+    const int c = c0 + lane;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), g = a;
+    if (c < H * 8) {
+      a = *reinterpret_cast<const uint4*>(o + base + c * 8);
+      g = *reinterpret_cast<const uint4*>(dout + base + c * 8);
+    }
+    float s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+              bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+              bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+    // the 8 chunks of one head sit in 8 consecutive lanes
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0 && c < H * 8) delta[(size_t(b) * H + (c >> 3)) * N + n] = s;
+  }
+}
+
+// dq_acc fp32 [B,N,H,64] -> bf16 q-slot of dqkv [B,N,3,H,64]
+__global__ void __launch_bounds__(256) attn_bwd_dq_store_kernel(const float* __restrict__ dq_acc,
+                                                                 __nv_bfloat16* __restrict__ dqkv, long long rows,
+                                                                 int H) {
+  const long long total = rows * H * 8;   // 8-element chunks
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / (H * 8);
+    const int c = int(idx % (H * 8));
+    const float4 a = *reinterpret_cast<const float4*>(dq_acc + size_t(idx) * 8);
+    const float4 b = *reinterpret_cast<const float4*>(dq_acc + size_t(idx) * 8 + 4);
+    uint4 w;
+    w.x = pack_bf16x2(a.x, a.y); w.y = pack_bf16x2(a.z, a.w);
+    w.z = pack_bf16x2(b.x, b.y); w.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(dqkv + size_t(row) * 3 * H * 64 + size_t(c) * 8) = w;
+  }
+}
+
+__global__ void __launch_bounds__(kAbThreads, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                     const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_base + kAbSmemBar;
+  const uint32_t kv_full = bar0, kv_empty = bar0 + 8;
+  auto qd_full = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto qd_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+  const uint32_t s_full = bar0 + 48, s_empty = bar0 + 56, p_full = bar0 + 64, pv_done = bar0 + 72, dq_empty = bar0 + 80,
+                 kvacc_full = bar0 + 88, kvacc_empty = bar0 + 96;
+  const uint32_t tmem_ptr_addr = smem_base + kAbSmemTmemPtr;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(qd_full(s), 1); mbar_init(qd_empty(s), 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    mbar_init(dq_empty, 4); mbar_init(kvacc_full, 1); mbar_init(kvacc_empty, 4);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 5) tmem_alloc<1>(tmem_ptr_addr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kAbSmemTmemPtr);
+  const int H = p.H, NT = p.num_t;
+
+  if (warp == 4) {
+    // =============================== TMA loader =================================
+    if (lane == 0) {
+      uint32_t n_item = 0, n_pair = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n_item) {
+        const int j = item % NT, bh = item / NT, h = bh % H, b = bh / H;
+        mbar_wait(kv_empty, (n_item & 1u) ^ 1u);
+        mbar_arrive_expect_tx(kv_full, 2 * kAbT);
+        tma_load_4d(smem_base + kAbSmemK, &tm_qkv, kv_full, 0, H + h, j * 128, b, kEvictLast);
+        tma_load_4d(smem_base + kAbSmemV, &tm_qkv, kv_full, 0, 2 * H + h, j * 128, b, kEvictLast);
+        for (int i = 0; i < NT; ++i, ++n_pair) {
+          const int st = int(n_pair & 1u);
+          mbar_wait(qd_empty(st), ((n_pair >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(qd_full(st), 2 * kAbT);
+          tma_load_4d(smem_base + kAbSmemQ + st * kAbT, &tm_qkv, qd_full(st), 0, h, i * 128, b, kEvictLast);
+          tma_load_4d(smem_base + kAbSmemDO + st * kAbT, &tm_do, qd_full(st), 0, h, i * 128, b, kEvictLast);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer =================================
+    if (lane == 0) {
+      constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);    // K-major x K-major
+      constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);    // A K-major (P^T / dS^T), B MN-major (dO / Q)
+      constexpr uint32_t id_dq = make_idesc_bf16(128, 64, 1, 1);    // A = dS read MN-major, B = K MN-major
+      uint32_t n_item = 0, n_pair = 0;
+      const uint64_t k_desc = make_smem_desc_sw128(smem_base + kAbSmemK);
+      const uint64_t v_desc = make_smem_desc_sw128(smem_base + kAbSmemV);
+      const uint64_t p_desc = make_smem_desc_sw128(smem_base + kAbSmemP);
+      const uint64_t ds_desc = make_smem_desc_sw128(smem_base + kAbSmemDS);
+      // dS^T tile read as an MN-major A operand: the two 64-query column blocks are 16 KB apart (leading offset)
+      const uint64_t ds_mn_desc = make_smem_desc_sw128(smem_base + kAbSmemDS, 1024, 2 * 8192);
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n_item) {
+        mbar_wait(kv_full, n_item & 1u);
+        for (int i = 0; i < NT; ++i, ++n_pair) {
+          const int st = int(n_pair & 1u);
+          const uint64_t q_desc = make_smem_desc_sw128(smem_base + kAbSmemQ + st * kAbT);
+          const uint64_t do_desc = make_smem_desc_sw128(smem_base + kAbSmemDO + st * kAbT);
+          mbar_wait(qd_full(st), (n_pair >> 1) & 1u);
+          mbar_wait(s_empty, (n_pair & 1u) ^ 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // S^T = K Q^T
+            umma_f16_ss<1>(tmem_base + kAbTmS, k_desc + uint64_t(2 * k), q_desc + uint64_t(2 * k), id_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dP^T = V dO^T
+            umma_f16_ss<1>(tmem_base + kAbTmDP, v_desc + uint64_t(2 * k), do_desc + uint64_t(2 * k), id_s, k > 0);
+          umma_commit(s_full);
+          mbar_wait(p_full, n_pair & 1u);
+          if (i == 0) mbar_wait(kvacc_empty, (n_item & 1u) ^ 1u);
+          mbar_wait(dq_empty, (n_pair & 1u) ^ 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {   // 16 queries per step: A chunk (k/4) 16 KB further, 32 B per step; B 2 KB per step
+            const uint64_t a_off = uint64_t((k >> 2) * (kAbT >> 4) + 2 * (k & 3));
+            const uint64_t b_off = uint64_t(k * (2048 >> 4));
+            umma_f16_ss<1>(tmem_base + kAbTmDV, p_desc + a_off, do_desc + b_off, id_kv, (i > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ss<1>(tmem_base + kAbTmDK, ds_desc + a_off, q_desc + b_off, id_kv, (i > 0 || k > 0) ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {   // dQ = dS K: 16 keys (= 16 smem rows = 2 KB) per step on both operands
+            const uint64_t off = uint64_t(k * (2048 >> 4));
+            umma_f16_ss<1>(tmem_base + kAbTmDQ, ds_mn_desc + off, k_desc + off, id_dq, k > 0);
+          }
+          umma_commit(pv_done);
+          umma_commit(qd_empty(st));
+        }
+        umma_commit(kvacc_full);
+        umma_commit(kv_empty);
+      }
+    }
+  } else {
+    // =============================== compute warps ==============================
+    const int q4 = warp;                     // TMEM lane quarter
+    const int r = 32 * q4 + lane;            // row inside the tile (key row for S^T/dP^T/dK/dV, query row for dQ)
+    const uint32_t lane_off = uint32_t(32 * q4) << 16;
+    const uint32_t row_smem = uint32_t(r * 128);
+    const uint32_t swz = uint32_t(r & 7);
+    float* stat = reinterpret_cast<float*>(smem_gen + kAbSmemStat);
+    uint32_t n_item = 0, n_pair = 0;
+    const float c = p.scale_log2, sc = p.scale;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n_item) {
+      const int j = item % NT, bh = item / NT, h = bh % H, b = bh / H;
+      const bool key_ok = (j * 128 + r) < p.N;
+      for (int i = 0; i < NT; ++i, ++n_pair) {
+        // stage lse2 / delta of this query tile (padded queries: +inf / 0 -> P = 0)
+        float* st_l = stat + (n_pair & 1u) * 256;
+        {
+          const int qi = i * 128 + r;
+          const size_t off = (size_t(b) * H + h) * p.N + qi;
+          st_l[r] = (qi < p.N) ? p.lse2[off] : INFINITY;
+          st_l[128 + r] = (qi < p.N) ? p.delta[off] : 0.f;
+        }
+        named_bar_sync(1, 128);
+        mbar_wait(s_full, n_pair & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t s[64], dp[64];
+          tmem_ld_32x32b_x32_at<0>(tmem_base + lane_off + kAbTmS + uint32_t(64 * hf), s);
+          tmem_ld_32x32b_x32_at<32>(tmem_base + lane_off + kAbTmS + uint32_t(64 * hf + 32), s);
+          tmem_ld_32x32b_x32_at<0>(tmem_base + lane_off + kAbTmDP + uint32_t(64 * hf), dp);
+          tmem_ld_32x32b_x32_at<32>(tmem_base + lane_off + kAbTmDP + uint32_t(64 * hf + 32), dp);
+          tmem_wait_ld();
+          if (hf == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {   // eight 16-byte groups = 8 queries each
+            uint32_t pp[4], dd[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c0 = 8 * g + 2 * e;
+              const float2 l2 = *reinterpret_cast<const float2*>(st_l + 64 * hf + c0);
+              const float2 dl = *reinterpret_cast<const float2*>(st_l + 128 + 64 * hf + c0);
+              float p0 = ex2f(fmaf(__uint_as_float(s[c0]), c, -l2.x));
+              float p1 = ex2f(fmaf(__uint_as_float(s[c0 + 1]), c, -l2.y));
+              if (!key_ok) { p0 = 0.f; p1 = 0.f; }
+              const float d0 = p0 * (__uint_as_float(dp[c0]) - dl.x) * sc;
+              const float d1 = p1 * (__uint_as_float(dp[c0 + 1]) - dl.y) * sc;
+              pp[e] = pack_bf16x2(p0, p1);
+              dd[e] = pack_bf16x2(d0, d1);
+            }
+            const uint32_t a = row_smem + uint32_t(hf * kAbT) + ((uint32_t(g) ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemP + a), "r"(pp[0]),
+                         "r"(pp[1]), "r"(pp[2]), "r"(pp[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemDS + a), "r"(dd[0]),
+                         "r"(dd[1]), "r"(dd[2]), "r"(dd[3]) : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // ---- dQ partial of this (key tile, query tile) pair -> fp32 accumulator in HBM ----
+        mbar_wait(pv_done, n_pair & 1u);   // also: P^T / dS^T smem may be overwritten from here on
+        tc_fence_after();
+        {
+          const int qi = i * 128 + r;
+          float* dst = p.dq_acc + ((size_t(b) * p.N + qi) * H + h) * 64;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDQ + uint32_t(32 * hh), o);
+            tmem_wait_ld();
+            if (qi < p.N) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32 * hh + e),
+                             "f"(__uint_as_float(o[e])), "f"(__uint_as_float(o[e + 1])),
+                             "f"(__uint_as_float(o[e + 2])), "f"(__uint_as_float(o[e + 3])) : "memory");
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_empty);
+        }
+      }
+      // ---- dK_j, dV_j leave TMEM once per item ----
+      mbar_wait(kvacc_full, n_item & 1u);
+      tc_fence_after();
+      {
+        const int kv = j * 128 + r;
+        __nv_bfloat16* base = p.dqkv + ((size_t(b) * p.N + kv) * 3) * H * 64 + size_t(h) * 64;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {   // 0: dK (slot 1), 1: dV (slot 2)
+          const uint32_t tcol = which == 0 ? kAbTmDK : kAbTmDV;
+          __nv_bfloat16* dst = base + size_t(which + 1) * H * 64;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_off + tcol + uint32_t(32 * hh), o);
+            tmem_wait_ld();
+            if (key_ok) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 8) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(o[e]), __uint_as_float(o[e + 1]));
+                w.y = pack_bf16x2(__uint_as_float(o[e + 2]), __uint_as_float(o[e + 3]));
+                w.z = pack_bf16x2(__uint_as_float(o[e + 4]), __uint_as_float(o[e + 5]));
+                w.w = pack_bf16x2(__uint_as_float(o[e + 6]), __uint_as_float(o[e + 7]));
+                *reinterpret_cast<uint4*>(dst + 32 * hh + e) = w;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(kvacc_empty);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<1>(tmem_base, 512);
+}
+
+}  // namespace mt
+
+extern "C" int mt_attention_bwd_workspace_bytes(int B, int N, int H, size_t* bytes) {
+  using namespace mt;
+  MT_REQUIRE(bytes && B > 0 && N > 0 && H > 0, MT_ERR_BAD_SHAPE, "mt_attention_bwd_workspace_bytes: bad arguments");
+  *bytes = size_t(B) * N * H * 64 * 4 + size_t(B) * H * N * 4 + 256;
+  return MT_OK;
+}
+
+extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                                void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale,
+                                void* stream) {
+  using namespace mt;
+  MT_REQUIRE(qkv && out && dout && lse2 && dqkv && workspace, MT_ERR_BAD_SHAPE, "mt_attention_bwd: null pointer");
+  MT_REQUIRE(B > 0 && N > 0 && H > 0, MT_ERR_BAD_SHAPE, "mt_attention_bwd: B, N, H must be positive");
+  MT_REQUIRE(dh == 64, MT_ERR_UNSUPPORTED, "mt_attention_bwd: head_dim %d not supported (only 64)", dh);
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) |
+               reinterpret_cast<uintptr_t>(dqkv) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_attention_bwd: pointers must be 16-byte aligned");
+  const size_t dq_bytes = size_t(B) * N * H * 64 * 4;
+  const size_t need = dq_bytes + size_t(B) * H * N * 4 + 256;
+  MT_REQUIRE(workspace_bytes >= need, MT_ERR_BAD_SHAPE, "mt_attention_bwd: workspace too small (%zu < %zu)",
+             workspace_bytes, need);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* dq_acc = reinterpret_cast<float*>(workspace);
+  float* delta = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((dq_bytes + 255) / 256) * 256);
+  MT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
+  {
+    const long long rows = (long long)B * N;
+    attn_bwd_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                                  reinterpret_cast<const __nv_bfloat16*>(dout), delta,
+                                                                  B, N, H);
+    MT_CHECK_CUDA(cudaGetLastError());
+  }
+  CUtensorMap tm_qkv, tm_do;
+  {
+    uint64_t dims[4] = {64, uint64_t(3 * H), uint64_t(N), uint64_t(B)};
+    uint64_t strides[3] = {64 * 2, uint64_t(3 * H) * 64 * 2, uint64_t(N) * 3 * H * 64 * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int rc = encode_tmap(&tm_qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, qkv, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {64, uint64_t(H), uint64_t(N), uint64_t(B)};
+    uint64_t strides[3] = {64 * 2, uint64_t(H) * 64 * 2, uint64_t(N) * H * 64 * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int rc = encode_tmap(&tm_do, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dout, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnBwdParams p;
+  p.B = B; p.N = N; p.H = H;
+  p.num_t = ceil_div(N, 128);
+  p.num_items = B * H * p.num_t;
+  p.scale = scale;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse2 = lse2;
+  p.delta = delta;
+  p.dq_acc = dq_acc;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const int grid = p.num_items < sms ? p.num_items : sms;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+    attr_set = true;
+  }
+  attention_bwd_kernel<<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, p);
+  MT_CHECK_CUDA(cudaGetLastError());
+  {
+    const long long rows = (long long)B * N;
+    long long blocks = (rows * H * 8 + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    attn_bwd_dq_store_kernel<<<unsigned(blocks), 256, 0, s>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dqkv), rows, H);
+    MT_CHECK_CUDA(cudaGetLastError());
+  }
+  return MT_OK;
+}

@@ -95,7 +95,61 @@ __global__ void __launch_bounds__(256) gelu_kernel(const __nv_bfloat16* __restri
   }
 }
 
+// dst[c, r] = src[r, c]; dst has leading dimension ldd >= R (columns R..ldd-1 are zero-filled) so that the result can
+// feed the TN GEMM (row pitch must be a multiple of 16 bytes).  32x32 tiles through padded shared memory.
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src,
+                                                              __nv_bfloat16* __restrict__ dst, int R, int C, int ldd) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    tile[ty + 8 * k][tx] = (r < R && c < C) ? src[size_t(r) * C + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k, r = r0 + tx;
+    if (c < C && r < ldd) dst[size_t(c) * ldd + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+// out[n] += sum_m x[m, n]   (out must be zero-initialised; fp32 atomics across row chunks)
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int M,
+                                                      int N) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= N) return;
+  float s = 0.f;
+  for (int r = blockIdx.y; r < M; r += gridDim.y) s += __bfloat162float(x[size_t(r) * N + col]);
+  atomicAdd(out + col, s);
+}
+
 }  // namespace mt
+
+extern "C" int mt_transpose_bf16(const void* src, void* dst, int R, int C, int ldd, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(src && dst, MT_ERR_BAD_SHAPE, "mt_transpose_bf16: null pointer");
+  MT_REQUIRE(R > 0 && C > 0 && ldd >= R, MT_ERR_BAD_SHAPE, "mt_transpose_bf16: need R, C > 0 and ldd >= R");
+  dim3 grid(unsigned(ceil_div(C, 32)), unsigned(ceil_div(ldd, 32)));
+  transpose_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), R, C, ldd);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+extern "C" int mt_colsum(const void* x, float* out, int M, int N, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && out, MT_ERR_BAD_SHAPE, "mt_colsum: null pointer");
+  MT_REQUIRE(M > 0 && N > 0, MT_ERR_BAD_SHAPE, "mt_colsum: M and N must be positive");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MT_CHECK_CUDA(cudaMemsetAsync(out, 0, size_t(N) * 4, s));
+  int chunks = M < 512 ? 1 : (M / 256 > 592 ? 592 : M / 256);
+  dim3 grid(unsigned(ceil_div(N, 256)), unsigned(chunks));
+  colsum_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, M, N);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
 
 extern "C" int mt_layernorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const void* add,
                                 void* dx, int M, int d, void* stream) {

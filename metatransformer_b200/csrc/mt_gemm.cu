@@ -157,6 +157,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
@@ -419,19 +422,8 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
     MT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(unsigned(clusters * CG), 1, 1);
-  cfg.blockDim = dim3(kGemmThreads, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = CG;
-  attrs[0].val.clusterDim.y = 1;
-  attrs[0].val.clusterDim.z = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = 1;
-  MT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a, tm_b, tm_y, p));
+  MT_CHECK_CUDA(launch_pdl(kern, dim3(unsigned(clusters * CG), 1, 1), dim3(kGemmThreads, 1, 1), size_t(Cfg::kSmemBytes),
+                           stream, unsigned(CG), tm_a, tm_b, tm_y, p));
   return MT_OK;
 }
 

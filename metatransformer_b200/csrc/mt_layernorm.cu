@@ -40,6 +40,8 @@ layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma, con
                  __nv_bfloat16* __restrict__ y, int M, int d, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= M) return;
   const TIn* xr = x + size_t(row) * d;
   __nv_bfloat16* yr = y + size_t(row) * d;
@@ -114,6 +116,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 row_stats_kernel(const TIn* __restrict__ x, float2* __restrict__ stats, int M, int d, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= M) return;
   const TIn* xr = x + size_t(row) * d;
   const float inv_d = 1.0f / float(d);
@@ -155,14 +159,15 @@ row_stats_kernel(const TIn* __restrict__ x, float2* __restrict__ stats, int M, i
 }
 
 template <typename TIn>
-static void launch_row_stats(const void* x, float* stats, int M, int d, float eps, cudaStream_t s) {
+static int launch_row_stats(const void* x, float* stats, int M, int d, float eps, cudaStream_t s) {
   const TIn* xp = reinterpret_cast<const TIn*>(x);
   float2* sp = reinterpret_cast<float2*>(stats);
   const unsigned grid = unsigned(ceil_div(M, kLnWarps));
   const unsigned block = kLnWarps * 32;
-  if (d == 768) row_stats_kernel<3, TIn><<<grid, block, 0, s>>>(xp, sp, M, d, eps);
-  else if (d == 1024) row_stats_kernel<4, TIn><<<grid, block, 0, s>>>(xp, sp, M, d, eps);
-  else row_stats_kernel<0, TIn><<<grid, block, 0, s>>>(xp, sp, M, d, eps);
+  if (d == 768) MT_CHECK_CUDA(launch_pdl(row_stats_kernel<3, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps));
+  else if (d == 1024) MT_CHECK_CUDA(launch_pdl(row_stats_kernel<4, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps));
+  else MT_CHECK_CUDA(launch_pdl(row_stats_kernel<0, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps));
+  return MT_OK;
 }
 
 // One-time weight preparation for the folded form of  Linear(LayerNorm(x)):
@@ -201,10 +206,9 @@ static int launch_ln(const void* x, const float* gamma, const float* beta, void*
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   const unsigned grid = unsigned(ceil_div(M, kLnWarps));
   const unsigned block = kLnWarps * 32;
-  if (d == 768) layernorm_kernel<3, TIn><<<grid, block, 0, s>>>(xp, gamma, beta, yp, M, d, eps);
-  else if (d == 1024) layernorm_kernel<4, TIn><<<grid, block, 0, s>>>(xp, gamma, beta, yp, M, d, eps);
-  else layernorm_kernel<0, TIn><<<grid, block, 0, s>>>(xp, gamma, beta, yp, M, d, eps);
-  MT_CHECK_CUDA(cudaGetLastError());
+  if (d == 768) MT_CHECK_CUDA(launch_pdl(layernorm_kernel<3, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, gamma, beta, yp, M, d, eps));
+  else if (d == 1024) MT_CHECK_CUDA(launch_pdl(layernorm_kernel<4, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, gamma, beta, yp, M, d, eps));
+  else MT_CHECK_CUDA(launch_pdl(layernorm_kernel<0, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, gamma, beta, yp, M, d, eps));
   return MT_OK;
 }
 
@@ -233,14 +237,10 @@ extern "C" int mt_row_stats(const void* x, int x_dtype, float* stats, int M, int
   MT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
              MT_ERR_BAD_ALIGN, "mt_row_stats: x must be 16-byte and stats 8-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (x_dtype == MT_DT_BF16) launch_row_stats<__nv_bfloat16>(x, stats, M, d, eps, s);
-  else if (x_dtype == MT_DT_F32) launch_row_stats<float>(x, stats, M, d, eps, s);
-  else {
-    set_error("mt_row_stats: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
-    return MT_ERR_BAD_DTYPE;
-  }
-  MT_CHECK_CUDA(cudaGetLastError());
-  return MT_OK;
+  if (x_dtype == MT_DT_BF16) return launch_row_stats<__nv_bfloat16>(x, stats, M, d, eps, s);
+  if (x_dtype == MT_DT_F32) return launch_row_stats<float>(x, stats, M, d, eps, s);
+  set_error("mt_row_stats: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
+  return MT_ERR_BAD_DTYPE;
 }
 
 extern "C" int mt_fold_layernorm(const void* w, int w_dtype, const float* gamma, const float* beta, const float* bias,

@@ -301,6 +301,13 @@ MT_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 MT_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 MT_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still draining; pdl_wait() blocks until the predecessor has completed and
+// its memory is visible (call it before the first dependent global access), pdl_launch_dependents() lets the
+// successor's CTAs be scheduled as soon as SMs free up.
+MT_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+MT_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // packed fp32x2 arithmetic (sm_100): one issue slot for two lanes of FMA work
 MT_DEVINL uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;

@@ -153,6 +153,102 @@ def attention(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None,
     return out
 
 
+def attention_lse(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None):
+    """attention() that also returns lse2 [B,H,N] (fp32 log2-sum-exp of the scaled scores) for the backward."""
+    _require_cuda(qkv)
+    B, N, C3 = qkv.shape
+    dh = C3 // (3 * num_heads)
+    if scale is None:
+        scale = dh ** -0.5
+    out = torch.empty((B, N, num_heads * dh), dtype=torch.bfloat16, device=qkv.device)
+    lse2 = torch.empty((B, num_heads, N), dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(_lib.load().mt_attention_fwd_lse(qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, num_heads, dh,
+                                               float(scale), _stream()), "mt_attention_fwd_lse")
+    return out, lse2
+
+
+def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse2: torch.Tensor, num_heads: int,
+                  scale: Optional[float] = None) -> torch.Tensor:
+    """d(qkv) [B,N,3*H*dh] bf16 of attention(); `out`/`lse2` are the forward's results, `dout` the gradient of `out`."""
+    import ctypes
+    _require_cuda(qkv, out, dout, lse2)
+    B, N, C3 = qkv.shape
+    dh = C3 // (3 * num_heads)
+    if scale is None:
+        scale = dh ** -0.5
+    dqkv = torch.empty_like(qkv)
+    need = ctypes.c_size_t()
+    lib = _lib.load()
+    check(lib.mt_attention_bwd_workspace_bytes(B, N, num_heads, ctypes.byref(need)), "mt_attention_bwd_workspace_bytes")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.mt_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), B, N, num_heads, dh, float(scale), _stream()),
+              "mt_attention_bwd")
+    return dqkv
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, gamma: Optional[torch.Tensor] = None,
+                  add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx of LayerNorm: add + rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma (gamma None: already applied)."""
+    _require_cuda(dy, x, stats, gamma, add)
+    M, d = x.shape
+    dx = torch.empty((M, d), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_layernorm_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), _ptr(gamma), _ptr(add),
+                                           dx.data_ptr(), M, d, _stream()), "mt_layernorm_bwd")
+    return dx
+
+
+def gelu(u: torch.Tensor) -> torch.Tensor:
+    """h = gelu(u) (exact erf), bf16."""
+    _require_cuda(u)
+    h = torch.empty_like(u)
+    with torch.cuda.device(u.device):
+        check(_lib.load().mt_gelu(u.data_ptr(), h.data_ptr(), u.numel(), _stream()), "mt_gelu")
+    return h
+
+
+def linear_gelu_grad(dy: torch.Tensor, weight_t: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """(dy @ weight_t.T) * gelu'(u): backward through fc2 and the GELU in one GEMM (weight_t = fc2.weight.T, [hidden, d])."""
+    _require_cuda(dy, weight_t, u)
+    M, K = dy.shape
+    N = weight_t.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=dy.device)
+    with torch.cuda.device(dy.device):
+        check(_lib.load().mt_gemm_bf16(dy.data_ptr(), weight_t.data_ptr(), None, u.data_ptr(), out.data_ptr(), M, N, K, 2,
+                                       0, _stream()), "mt_gemm_bf16(act=2)")
+    return out
+
+
+def transpose(x: torch.Tensor, pad_to: int = 8) -> torch.Tensor:
+    """x [R,C] bf16 -> [C, ceil(R/pad_to)*pad_to] (zero padded): operand layout for the weight-gradient GEMM."""
+    _require_cuda(x)
+    R, C = x.shape
+    ldd = (R + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((C, ldd), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_transpose_bf16(x.data_ptr(), out.data_ptr(), R, C, ldd, _stream()), "mt_transpose_bf16")
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 column sums of x [M,N] bf16 (bias gradient)."""
+    _require_cuda(x)
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_colsum(x.data_ptr(), out.data_ptr(), M, N, _stream()), "mt_colsum")
+    return out
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW [N,K] = dy[M,N]^T @ x[M,K] (bf16 in, fp32 accumulate over M, bf16 out) via transposed copies + the TN GEMM."""
+    dyt, xt = transpose(dy), transpose(x)          # [N, Mp], [K, Mp]
+    return linear(dyt, xt)
+
+
 def im2row(x: torch.Tensor, kernel: Sequence[int], stride: Sequence[int]) -> Tuple[torch.Tensor, Tuple[int, int, int]]:
     """x [B,C,T,H,W] (fp32/bf16) -> rows [B*Tp*Hp*Wp, C*kt*kh*kw] bf16 and (Tp,Hp,Wp)."""
     _require_cuda(x)

@@ -65,9 +65,9 @@ def _check_input(x: torch.Tensor, what: str) -> None:
                            "fallback (use oracle/ for CPU reference numbers)")
     if x.dim() != 3:
         raise ValueError(f"{what}: expected (B, N, C) input, got shape {tuple(x.shape)}")
-    if torch.is_grad_enabled() and x.requires_grad:
-        raise NotImplementedError(f"{what}: backward through the B200 kernels (SURVEY.md §8a E8) is not implemented "
-                                  "yet; call under torch.no_grad()")
+    if torch.is_grad_enabled() and x.requires_grad and what != "Block":
+        raise NotImplementedError(f"{what}: autograd is implemented at Block granularity only (SURVEY.md §8a E8); "
+                                  "call the enclosing Block or use torch.no_grad()")
 
 
 def _to_bf16_2d(x: torch.Tensor) -> torch.Tensor:
@@ -219,11 +219,82 @@ class Block(nn.Module):
         return ops.linear(hid, _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16),
                           _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32), residual=x_mid)
 
+    def _transposed(self, name: str, w: torch.Tensor) -> torch.Tensor:
+        """bf16 [in, out] copy of a packed bf16 [out, in] weight: the B operand of the dgrad GEMM  dX = dY @ W."""
+        cache = self.__dict__.setdefault("_mt_pack_cache", {})
+        key = (w.data_ptr(), w._version, w.device)
+        hit = cache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        wt = w.t().contiguous()           # one-time weight preparation (plumbing, not on the per-step path)
+        cache[name] = (key, wt)
+        return wt
+
+    def _forward_train(self, x2: torch.Tensor, B: int, N: int):
+        """Forward that keeps what the backward needs (qkv, attention output + lse, the pre-GELU activation)."""
+        attn, mlp = self.attn, self.mlp
+        wq, csq, bq = self._folded("fold.qkv", attn.qkv, self.norm1)
+        stats1 = ops.row_stats(x2, self.norm1.eps)
+        qkv = ops.linear_ln(x2, wq, bq, csq, stats1)
+        o, lse2 = ops.attention_lse(qkv.view(B, N, -1), attn.num_heads, attn.scale)
+        x_mid = ops.linear(o.view(B * N, -1), _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16),
+                           _packed(attn, "proj.bias", attn.proj.bias, torch.float32), residual=x2)
+        w1, cs1, b1 = self._folded("fold.fc1", mlp.fc1, self.norm2)
+        stats2 = ops.row_stats(x_mid, self.norm2.eps)
+        u = ops.linear_ln(x_mid, w1, b1, cs1, stats2, gelu=False)
+        hid = ops.gelu(u)
+        out = ops.linear(hid, _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16),
+                         _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32), residual=x_mid)
+        return out, (x2, stats1, qkv, o, lse2, x_mid, stats2, u)
+
+    def _backward_2d(self, g2: torch.Tensor, saved, B: int, N: int) -> torch.Tensor:
+        """dX of the Block for frozen weights (dgrad only): 4 GEMMs + attention backward + 2 LayerNorm backwards."""
+        x2, stats1, qkv, o, lse2, x_mid, stats2, u = saved
+        attn, mlp = self.attn, self.mlp
+        M = B * N
+        w2t = self._transposed("t.fc2", _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16))
+        du = ops.linear_gelu_grad(g2, w2t, u)                                   # dL/du = (g W2) * gelu'(u)
+        w1f = self._folded("fold.fc1", mlp.fc1, self.norm2)[0]
+        dxh2 = ops.linear(du, self._transposed("t.fc1f", w1f))                  # dL/dxhat (gamma already folded in)
+        g1 = ops.layernorm_bwd(dxh2, x_mid, stats2, None, add=g2)               # + residual branch
+        wpt = self._transposed("t.proj", _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16))
+        do = ops.linear(g1, wpt)
+        dqkv = ops.attention_bwd(qkv.view(B, N, -1), o, do.view(B, N, -1), lse2, attn.num_heads, attn.scale)
+        wqf = self._folded("fold.qkv", attn.qkv, self.norm1)[0]
+        dxh1 = ops.linear(dqkv.view(M, -1), self._transposed("t.qkvf", wqf))
+        return ops.layernorm_bwd(dxh1, x2, stats1, None, add=g1)
+
     def forward(self, x):
         _check_input(x, "Block")
         self.attn._check_train()
         self.mlp._check_train()
         if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
             raise NotImplementedError("Block: drop_path > 0 in training mode is not implemented on the B200 path yet")
+        if torch.is_grad_enabled() and x.requires_grad:
+            if any(p.requires_grad for p in self.parameters()):
+                raise NotImplementedError("Block: weight gradients (fine-tuning the encoder, SURVEY.md §8f rank 1) are "
+                                          "not implemented yet; freeze the encoder (requires_grad_(False)) — the "
+                                          "input gradient for trainable tokenizers is supported")
+            return _BlockFn.apply(x, self)
         B, N, C = x.shape
         return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N), x)
+
+
+class _BlockFn(torch.autograd.Function):
+    """Autograd node of one frozen Block: forward and input-gradient both run on the sm_100a kernels."""
+
+    @staticmethod
+    def forward(ctx, x, block):
+        B, N, C = x.shape
+        out2, saved = block._forward_train(_to_bf16_2d(x.detach()), B, N)
+        ctx.block, ctx.saved, ctx.shape, ctx.in_dtype = block, saved, (B, N, C), x.dtype
+        return _from_bf16(out2, x)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N, C = ctx.shape
+        g2 = _to_bf16_2d(g)
+        dx2 = ctx.block._backward_2d(g2, ctx.saved, B, N)
+        ctx.saved = None
+        dx = dx2 if ctx.in_dtype == torch.bfloat16 else ops.cast(dx2, ctx.in_dtype)
+        return dx.view(B, N, C), None

@@ -1,0 +1,125 @@
+"""GPU parity of the backward kernels against torch autograd of the fp64 CPU oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import encoder_oracle as orc  # noqa: E402
+from tests.test_gpu_parity import _assert_close, _bf16_round, mt  # noqa: E402,F401
+
+
+@pytest.mark.parametrize("B,N,H", [(1, 128, 1), (2, 100, 2), (2, 196, 3), (1, 256, 2), (1, 300, 1), (1, 520, 2)])
+def test_attention_backward_matches_autograd(mt, B, N, H):
+    g = torch.Generator().manual_seed(N * 3 + H)
+    C = H * 64
+    qkv = _bf16_round(torch.randn(B, N, 3 * C, generator=g))
+    dout = _bf16_round(torch.randn(B, N, C, generator=g))
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = (((q @ k.transpose(-2, -1)) * 0.125).softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+    ref.backward(dout.double())
+    out, lse2 = mt.ops.attention_lse(qkv.cuda().bfloat16(), H)
+    _assert_close(out, ref.detach(), what="attention fwd (lse variant)")
+    s = (q @ k.transpose(-2, -1)) * 0.125
+    lse_ref = torch.logsumexp(s.detach(), dim=-1) * 1.4426950408889634          # [B,H,N], base 2
+    assert (lse2.double().cpu() - lse_ref).abs().max() < 2e-2
+    dqkv = mt.ops.attention_bwd(qkv.cuda().bfloat16(), out, dout.cuda().bfloat16(), lse2, H)
+    _assert_close(dqkv, x.grad, rel=2e-2, mx=2e-2, what=f"attention bwd B={B} N={N} H={H}")
+
+
+@pytest.mark.parametrize("M,d,use_gamma,use_add", [(37, 768, False, True), (200, 1024, True, False), (5, 200, True, True)])
+def test_layernorm_backward_matches_autograd(mt, M, d, use_gamma, use_add):
+    g = torch.Generator().manual_seed(d + M)
+    x = _bf16_round(torch.randn(M, d, generator=g) * 2 + 0.3)
+    dy = _bf16_round(torch.randn(M, d, generator=g))
+    gamma = 1 + torch.randn(d, generator=g) * 0.2
+    add = _bf16_round(torch.randn(M, d, generator=g))
+    xx = x.double().requires_grad_(True)
+    w = gamma.double() if use_gamma else torch.ones(d, dtype=torch.float64)
+    orc.layer_norm(xx, w, torch.zeros(d, dtype=torch.float64), 1e-5).backward(dy.double())
+    ref = xx.grad + (add.double() if use_add else 0)
+    stats = mt.ops.row_stats(x.cuda().bfloat16(), 1e-5)
+    dx = mt.ops.layernorm_bwd(dy.cuda().bfloat16(), x.cuda().bfloat16(), stats, gamma.cuda() if use_gamma else None,
+                              add.cuda().bfloat16() if use_add else None)
+    _assert_close(dx, ref, what="layernorm bwd")
+
+
+def test_gelu_and_gelu_grad_gemm(mt):
+    g = torch.Generator().manual_seed(5)
+    M, d, hidden = 300, 256, 1024
+    u = _bf16_round(torch.randn(M, hidden, generator=g) * 1.5)
+    h = mt.ops.gelu(u.cuda().bfloat16())
+    _assert_close(h, orc.gelu_erf(u.double()), what="gelu")
+    dy = _bf16_round(torch.randn(M, d, generator=g))
+    w2 = _bf16_round(torch.randn(d, hidden, generator=g) * 0.05)          # fc2.weight [d, hidden]
+    uu = u.double().requires_grad_(True)
+    (orc.gelu_erf(uu) @ w2.double().t()).backward(dy.double())
+    got = mt.ops.linear_gelu_grad(dy.cuda().bfloat16(), w2.t().contiguous().cuda().bfloat16(), u.cuda().bfloat16())
+    _assert_close(got, uu.grad, what="fc2 dgrad * gelu'")
+
+
+def test_block_input_gradient_matches_oracle_autograd(mt):
+    """Frozen Base-16 Blocks, trainable input (the tokenizer's output): dL/dx through 2 Blocks vs fp64 autograd."""
+    depth = 2
+    sd = orc.make_encoder_state_dict(768, depth, seed=3)
+    sd = {k: (_bf16_round(v) if v.dim() == 2 else v) for k, v in sd.items()}
+    enc = mt.build_encoder("base", depth=depth)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda().eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(21)
+    x = _bf16_round(torch.randn(2, 196, 768, generator=g))
+    gy = _bf16_round(torch.randn(2, 196, 768, generator=g))
+    xr = x.double().requires_grad_(True)
+    yr = orc.encoder(xr, {k: v.double() for k, v in sd.items()}, depth, 12)
+    yr.backward(gy.double())
+    xg = x.cuda().bfloat16().requires_grad_(True)
+    y = enc(xg)
+    _assert_close(y, yr.detach(), what="training-mode forward")
+    y.backward(gy.cuda().bfloat16())
+    assert xg.grad is not None and xg.grad.dtype == torch.bfloat16
+    _assert_close(xg.grad, xr.grad, rel=2e-2, mx=2e-2, what="dL/dx through 2 frozen Blocks")
+    # unfrozen encoder: weight gradients are not built yet -> loud error, no silent wrong training
+    enc.requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="weight gradients"):
+        enc(xg)
+
+
+def test_transpose_and_colsum(mt):
+    g = torch.Generator().manual_seed(9)
+    x = _bf16_round(torch.randn(301, 96, generator=g))
+    xt = mt.ops.transpose(x.cuda().bfloat16())
+    assert xt.shape == (96, 304)
+    assert torch.equal(xt[:, :301].float().cpu(), x.t()) and float(xt[:, 301:].abs().max()) == 0.0
+    cs = mt.ops.colsum(x.cuda().bfloat16())
+    assert (cs.cpu() - x.sum(0)).abs().max() < 1e-3
+
+
+def test_trainable_tokenizer_under_frozen_encoder(mt):
+    """The AST training pattern (Audio/src/models/ast_models.py:66-70): encoder frozen, patch-embed conv trainable.
+    Gradients of the conv weight / bias through 2 frozen Blocks vs fp64 autograd of the oracle."""
+    depth = 2
+    sd = orc.make_encoder_state_dict(768, depth, seed=6)
+    sd = {k: (_bf16_round(v) if v.dim() == 2 else v) for k, v in sd.items()}
+    enc = mt.build_encoder("base", depth=depth)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda().eval().requires_grad_(False)
+    tok = mt.Data2Seq("image", 768).cuda()
+    with torch.no_grad():
+        tok.embed.proj.weight.copy_(_bf16_round(tok.embed.proj.weight.cpu()).cuda())
+    g = torch.Generator().manual_seed(31)
+    img = _bf16_round(torch.rand(2, 3, 224, 224, generator=g))
+    gy = _bf16_round(torch.randn(2, 196, 768, generator=g) * 0.1)
+    # oracle
+    w = tok.embed.proj.weight.detach().cpu().double().requires_grad_(True)
+    b = tok.embed.proj.bias.detach().cpu().double().requires_grad_(True)
+    t_ref = orc.patch_embed_2d(img.double(), w, b, (16, 16))
+    y_ref = orc.encoder(t_ref, {k: v.double() for k, v in sd.items()}, depth, 12)
+    y_ref.backward(gy.double())
+    # kernels
+    y = enc(tok(img.cuda()))
+    y.backward(gy.cuda())
+    gw, gb = tok.embed.proj.weight.grad, tok.embed.proj.bias.grad
+    assert gw is not None and gw.shape == tok.embed.proj.weight.shape and gb is not None
+    _assert_close(gw.reshape(768, -1), w.grad.reshape(768, -1), rel=3e-2, mx=3e-2, what="conv weight grad")
+    _assert_close(gb, b.grad, rel=3e-2, mx=3e-2, what="conv bias grad")
+    assert all(p.grad is None for p in enc.parameters())

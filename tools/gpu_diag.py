@@ -225,7 +225,23 @@ def group_prof_fc1():
     torch.cuda.synchronize()
 
 
-GROUPS = {"prof": group_prof, "prof_fc1": group_prof_fc1, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+def group_prof_fc2():
+    """fc2-shaped GEMM (K=3072, N=768, residual), cg=2: main-loop dominated"""
+    import torch
+    from metatransformer_b200 import ops
+    dev = "cuda"
+    M, N, K = 50176, 768, 3072
+    x = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    b = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.linear(x, w, b, r, cta_group=2, out=out)
+    torch.cuda.synchronize()
+
+
+GROUPS = {"prof": group_prof, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
 
 
 def main():
