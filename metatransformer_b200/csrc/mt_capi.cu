@@ -3,6 +3,7 @@
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 namespace mt {
@@ -66,6 +67,15 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const voi
     return MT_ERR_CUDA;
   }
   return MT_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MT_B200_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 int sm_count(int* out) {

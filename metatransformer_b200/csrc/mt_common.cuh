@@ -39,7 +39,11 @@ int sm_count(int* out);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Launch with programmatic dependent launch enabled (and an optional cluster dimension).
+// Launch with an optional cluster dimension and, when MT_B200_PDL=1, programmatic dependent launch.  PDL is OFF by
+// default: on the C2 encoder step it measured 3% slower than plain stream order (BENCH notes in DESIGN.md), the
+// device-side griddepcontrol instructions are no-ops without the launch attribute.
+bool pdl_enabled();
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      unsigned cluster_x, Args... args) {
@@ -50,9 +54,11 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   int n = 0;
-  attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[n].val.programmaticStreamSerializationAllowed = 1;
-  ++n;
+  if (pdl_enabled()) {
+    attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   if (cluster_x > 1) {
     attrs[n].id = cudaLaunchAttributeClusterDimension;
     attrs[n].val.clusterDim.x = cluster_x;
