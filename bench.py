@@ -176,7 +176,7 @@ def run_ours(args):
     enc = mt.build_encoder("base")
     enc.load_state_dict(sd, strict=True)
     enc = enc.to(dev).eval()
-    fused = mt.FusedEncoder(enc)
+    fused = mt.FusedEncoder(enc, use_cuda_graph=args.cuda_graph)
     NBUF = 4   # rotating inputs: 4 x 77 MB = 308 MB > 126 MB L2 (plus ~1.3 GB of intermediates written per step)
     g = torch.Generator().manual_seed(1234 + rank)
     xs = [torch.randn(B, N, D, generator=g).bfloat16().to(dev) for _ in range(NBUF)]
@@ -347,6 +347,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay each forward from a captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

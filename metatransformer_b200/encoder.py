@@ -35,9 +35,13 @@ def build_encoder(scale: str = "base", **overrides) -> nn.Sequential:
 class FusedEncoder(nn.Module):
     """Runs a Sequential of `Block`s through the C-ABI whole-encoder driver (inference / frozen-encoder forward)."""
 
-    def __init__(self, blocks: nn.Sequential, fold_layernorm: bool = True):
+    def __init__(self, blocks: nn.Sequential, fold_layernorm: bool = True, use_cuda_graph: bool = False):
         super().__init__()
         self.fold_layernorm = fold_layernorm
+        # replay the 84 / 168 launches of one forward from a captured CUDA graph (keyed by the buffers involved);
+        # only pays off when the caller re-uses its input / output buffers
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs = {}
         if len(blocks) == 0 or not all(isinstance(b, Block) for b in blocks):
             raise TypeError("FusedEncoder needs a non-empty nn.Sequential of metatransformer_b200 Blocks")
         self.blocks = blocks
@@ -135,9 +139,28 @@ class FusedEncoder(nn.Module):
         check(lib.mt_encoder_workspace_bytes(self._handle, B, N, ctypes.byref(need)), "mt_encoder_workspace_bytes")
         if self._ws is None or self._ws.numel() < need.value or self._ws.device != x.device:
             self._ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
-        with torch.cuda.device(x.device):
+            self._graphs.clear()
+
+        def launch():
             check(lib.mt_encoder_forward(self._handle, xb.data_ptr(), y.data_ptr(), B, N, self._ws.data_ptr(),
                                          self._ws.numel(), torch.cuda.current_stream().cuda_stream), "mt_encoder_forward")
+
+        with torch.cuda.device(x.device):
+            if not self.use_cuda_graph:
+                launch()
+            else:
+                key = (xb.data_ptr(), y.data_ptr(), B, N, self._handle_key)
+                g = self._graphs.get(key)
+                if g is None:
+                    launch()                         # warm-up outside capture (function attributes, lazy module load)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        launch()
+                    if len(self._graphs) > 16:
+                        self._graphs.clear()
+                    self._graphs[key] = g
+                g.replay()
         if x.dtype == torch.bfloat16:
             return y
         return ops.cast(y, x.dtype)
