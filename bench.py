@@ -323,7 +323,8 @@ def run_ours(args):
             "config": {"workload": "C2: Base-16 encoder forward (12 x Block, d=768, 12 heads), synthetic bf16 tokens "
                                    "(B,N,d)=(256,196,768) per GPU, seeded random weights",
                        "global_batch": B * world, "seq_len": N, "parallelism": f"dp{world} (replicas, no forward collective)",
-                       "l2": "4 rotating 77 MB input buffers (308 MB > 126 MB L2) + ~1.3 GB intermediates per step"},
+                       "l2": "4 rotating 77 MB input buffers (308 MB > 126 MB L2) + ~1.3 GB intermediates per step",
+                       "launch": "CUDA-graph replay of the per-forward launch sequence" if args.cuda_graph else "stream launches"},
             "tflops": flops_step * world * args.steps / (ms_total * 1e-3) / 1e12,
             "frac_of_sustained_peak": flops_step * args.steps / (ms_total * 1e-3) / 1e12 / sustained_tf,
             "clocks": clocks,
@@ -347,7 +348,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cuda-graph", action="store_true", help="replay each forward from a captured CUDA graph")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                    help="launch the kernels of each forward individually instead of replaying a captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -59,6 +59,24 @@ int mt_fold_layernorm(const void* w /* [N,K] */, int w_dtype, const float* gamma
 int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float* bias_folded, const float* colsum,
                     const float* row_stats, void* y, int M, int N, int K, int act, int cta_group, void* stream);
 
+/* General form of the two calls above.  `out_row_sums` lets a GEMM whose output is the next LayerNorm's input
+ * (proj+residual, fc2+residual) emit that LayerNorm's statistics from its epilogue: for every output row one partial
+ * (sum, sum of squares) pair per 128-column slice, layout [M][S][2] fp32 with S = 2*ceil(N/256) (plain stores, fixed
+ * order => deterministic, no zero-initialisation).  The consuming LN-folded GEMM takes them with
+ * ln_stats_are_sums = S (mean = sum/K, var = sumsq/K - mean^2): no separate statistics pass over HBM is needed.  */
+typedef struct {
+  const float* bias;            /* [N] or NULL */
+  const void* residual;         /* bf16 [M,N] or NULL (act 2: the saved pre-activation) */
+  int act;                      /* 0, 1 (GELU), 2 (times gelu'(residual)) */
+  const float* ln_colsum;       /* LN folding of the INPUT (with ln_row_stats), or NULL */
+  const float* ln_row_stats;    /* [M][2] (mean, rstd), or [M][S][2] partial sums if ln_stats_are_sums = S > 0 */
+  int ln_stats_are_sums;
+  float ln_eps;                 /* used when ln_stats_are_sums */
+  float* out_row_sums;          /* [M][2*ceil(N/256)][2] partial statistics of the OUTPUT rows, or NULL */
+  int cta_group;                /* 0 auto, 1, 2 */
+} mt_gemm_opts;
+int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int N, int K, const mt_gemm_opts* opts, void* stream);
+
 /* ---- E2: LayerNorm over the last dim, fp32 statistics, biased variance -------------------------------------
  * y[M,d] (bf16) = (x - mean) * rsqrt(var + eps) * gamma + beta;  x bf16 or fp32 (x_dtype), gamma/beta fp32.
  * Replaces norm1 / norm2 = nn.LayerNorm(d) of Block (attention.py:46,50; eps 1e-5 per README.md:131).       */

@@ -57,7 +57,12 @@ struct GemmParams {
   int act;                      // 0 = identity, 1 = exact-erf GELU, 2 = multiply by gelu'(resid) (backward)
   int num_m_tiles, num_n_tiles;
   // LayerNorm folded into the GEMM (see mt_fold_layernorm): y = rstd_m * (acc - mean_m * colsum_n) + bias_n
-  const float2* row_stats;      // [M] (mean, rstd) or nullptr
+  const float2* row_stats;      // [M] (mean, rstd) — or (sum, sum of squares) when ln_sums != 0 — or nullptr
+  int ln_sums;                  // > 0: row_stats holds ln_sums partial (sum, sum of squares) pairs per row, written by
+                                // the epilogue of the GEMM that produced this GEMM's input
+  float ln_eps;
+  float* out_row_sums;          // [M][2*num_n_tiles][2]: per-(row, 128-column slice) partial (sum, sum of squares) of
+                                // this GEMM's output, or nullptr (plain stores: deterministic, no zero-init)
   const float* colsum;          // [N] sum_k W'[n,k] (of the bf16-rounded folded weight) or nullptr
 };
 
@@ -255,12 +260,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         reinterpret_cast<float4*>(bias_s)[32 + lane] = c4;
         __syncwarp();
         if (p.row_stats != nullptr && row < p.M) {
-          const float2 st = p.row_stats[row];
+          float2 st;
+          if (p.ln_sums > 0) {   // partial (sum, sum of squares) per 128-column slice, fixed summation order
+            const float2* ps = p.row_stats + size_t(row) * p.ln_sums;
+            float sx = 0.f, sy = 0.f;
+            for (int i = 0; i < p.ln_sums; ++i) { const float2 t = ps[i]; sx += t.x; sy += t.y; }
+            const float inv_k = 1.0f / float(p.K);
+            const float mean = sx * inv_k;
+            st = make_float2(mean, rsqrtf(fmaxf(fmaf(sy, inv_k, -mean * mean), 0.f) + p.ln_eps));
+          } else {
+            st = p.row_stats[row];
+          }
           ln_rstd = st.y;
           ln_nmr = -st.x * st.y;
         }
       }
       const uint64_t ln_rstd2 = pack_f32x2(ln_rstd, ln_rstd), ln_nmr2 = pack_f32x2(ln_nmr, ln_nmr);
+      uint64_t rs2 = pack_f32x2(0.f, 0.f), rss2 = rs2;   // running (sum, sum of squares) of this thread's output row
       // residual slices are fetched one 32-column slice ahead of their use (the first one before the accumulator
       // is even ready), so the L2/HBM latency hides behind the MMAs of this tile and the math of the previous slice
       const bool row_ok = (p.resid != nullptr) && (row < p.M);
@@ -330,6 +346,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             v01 = add_f32x2(v01, pack_f32x2(bf16_lo(r01), bf16_hi(r01)));
             v23 = add_f32x2(v23, pack_f32x2(bf16_lo(r23), bf16_hi(r23)));
           }
+          if (p.out_row_sums != nullptr) {
+            // LayerNorm statistics of the NEXT layer's input, gathered while the row is in registers (fp32 values
+            // before the bf16 rounding: the difference is O(2^-9/sqrt(d)) on the mean)
+            rs2 = add_f32x2(rs2, add_f32x2(v01, v23));
+            rss2 = fma_f32x2(v01, v01, fma_f32x2(v23, v23, rss2));
+          }
           float v0, v1, v2, v3;
           unpack_f32x2(v01, v0, v1);
           unpack_f32x2(v23, v2, v3);
@@ -355,6 +377,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           store_pending = true;
         }
       }
+      if (p.out_row_sums != nullptr && row < p.M) {
+        float a0, a1, q0, q1;
+        unpack_f32x2(rs2, a0, a1);
+        unpack_f32x2(rss2, q0, q1);
+        float2* dst = reinterpret_cast<float2*>(p.out_row_sums) + size_t(row) * (2 * p.num_n_tiles) + (2 * n_tile + hf);
+        *dst = make_float2(a0 + a1, q0 + q1);
+      }
       if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -373,7 +402,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 template <int CG>
 static int launch_gemm(const void* x, const void* w, const float* bias, const void* resid, int ldr, void* y, int M,
-                       int N, int K, int act, const float* row_stats, const float* colsum, cudaStream_t stream) {
+                       int N, int K, int act, const float* row_stats, const float* colsum, int ln_sums, float ln_eps,
+                       float* out_row_sums, cudaStream_t stream) {
   using Cfg = GemmCfg<CG>;
   CUtensorMap tm_a, tm_b, tm_y;
   {
@@ -405,6 +435,9 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   p.act = act;
   p.row_stats = reinterpret_cast<const float2*>(row_stats);
   p.colsum = colsum;
+  p.ln_sums = ln_sums;
+  p.ln_eps = ln_eps;
+  p.out_row_sums = out_row_sums;
   p.num_m_tiles = ceil_div(M, kBM * CG);
   p.num_n_tiles = ceil_div(N, kBN);
 
@@ -431,7 +464,7 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
 
 static int gemm_entry(const char* who, const void* x, const void* w, const float* bias, const void* residual, void* y,
                       int M, int N, int K, int act, const float* row_stats, const float* colsum, int cta_group,
-                      void* stream) {
+                      void* stream, int ln_sums = 0, float ln_eps = 0.f, float* out_row_sums = nullptr) {
   using namespace mt;
   MT_REQUIRE(x && w && y, MT_ERR_BAD_SHAPE, "%s: null pointer", who);
   MT_REQUIRE(M > 0 && N > 0 && K > 0, MT_ERR_BAD_SHAPE, "%s: M,N,K must be positive (got %d,%d,%d)", who, M, N, K);
@@ -458,8 +491,11 @@ static int gemm_entry(const char* who, const void* x, const void* w, const float
     }
     cta_group = auto_cg;
   }
-  if (cta_group == 1) return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, s);
-  if (cta_group == 2) return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, s);
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(out_row_sums) & 7) == 0, MT_ERR_BAD_ALIGN, "%s: out_row_sums must be 8-byte aligned", who);
+  if (cta_group == 1)
+    return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s);
+  if (cta_group == 2)
+    return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s);
   set_error("%s: cta_group must be 0 (auto), 1 or 2", who);
   return MT_ERR_UNSUPPORTED;
 }
@@ -478,4 +514,14 @@ extern "C" int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float*
   }
   return gemm_entry("mt_gemm_bf16_ln", x, w_folded, bias_folded, nullptr, y, M, N, K, act, row_stats, colsum, cta_group,
                     stream);
+}
+
+extern "C" int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int N, int K, const mt_gemm_opts* o,
+                               void* stream) {
+  if (!o) {
+    mt::set_error("mt_gemm_bf16_ex: opts is required");
+    return MT_ERR_BAD_SHAPE;
+  }
+  return gemm_entry("mt_gemm_bf16_ex", x, w, o->bias, o->residual, y, M, N, K, o->act, o->ln_row_stats, o->ln_colsum,
+                    o->cta_group, stream, o->ln_stats_are_sums, o->ln_eps, o->out_row_sums);
 }

@@ -222,7 +222,10 @@ def test_base16_encoder_matches_oracle_c1_shape(mt):
         y2 = enc(x.cuda().bfloat16())
     assert y.dtype == torch.bfloat16
     _assert_close(y, ref, rel=1e-2, mx=3e-2, what="Base-16 x12 fused")
-    assert torch.equal(y, y2), "per-Block path and fused driver must launch the same kernels on the same data"
+    # per-Block path (row-statistics kernel per LayerNorm) vs fused driver (statistics accumulated in the previous
+    # GEMM's epilogue): same math, different summation order
+    _assert_close(y2, ref, rel=1e-2, mx=3e-2, what="Base-16 x12 per-Block")
+    _assert_close(y, y2.float(), rel=1e-2, mx=3e-2, what="fused vs per-Block")
     # the un-folded sequence (LayerNorm kernel + plain GEMM) must agree with the oracle as well
     with torch.no_grad():
         y3 = mt.FusedEncoder(enc, fold_layernorm=False)(x.cuda().bfloat16())
