@@ -119,6 +119,12 @@ int mt_attention_bwd(const void* qkv, const void* out, const void* dout, const f
 int mt_im2row(const void* x, int x_dtype, void* rows, int B, int C, int T, int H, int W,
               int kt, int kh, int kw, int st, int sh, int sw, void* stream);
 
+/* ---- T4: time-series / IMU token embedding --------------------------------------------------------------------
+ * Circular Conv1d(c_in, d, k=3, padding=1) of TokenEmbedding (Data2Seq/Time_Series.py:29-42) as im2row + GEMM:
+ * x [B,T,C] -> rows bf16 [B*T, Kp], rows[b*T+t, c*3+kk] = x[b, (t+kk-1) mod T, c], zero-padded to Kp (% 8 == 0).
+ * The sinusoid positional embedding (Time_Series.py:8-26) is added by the GEMM's residual input.               */
+int mt_im2row1d_circular(const void* x, int x_dtype, void* rows, int B, int T, int C, int Kp, void* stream);
+
 /* ---- dtype conversion helper (weights packing, fp32 activations at the boundary) ---- */
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 

@@ -106,7 +106,57 @@ static int launch_im2row(const void* x, void* rows, const Im2RowParams& p, cudaS
   return MT_OK;
 }
 
+// Circular 1-D im2row of TokenEmbedding (Data2Seq/Time_Series.py:29-42): Conv1d(c_in, d, k=3, padding=1,
+// padding_mode='circular') over time.  rows[b*T + t, c*3 + kk] = x[b, (t + kk - 1) mod T, c]  (K order (c, kk) =
+// weight.view(d, -1)); columns 3*C .. Kp-1 are zero so that the row pitch is a multiple of 16 bytes.
+template <typename TIn>
+__global__ void __launch_bounds__(256) im2row1d_circular_kernel(const TIn* __restrict__ x,
+                                                                 __nv_bfloat16* __restrict__ rows, int B, int T, int C,
+                                                                 int Kp) {
+  const long long total = (long long)B * T * Kp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = int(idx % Kp);
+    const long long m = idx / Kp;
+    float v = 0.f;
+    if (k < 3 * C) {
+      const int c = k / 3, kk = k % 3;
+      const int t = int(m % T), b = int(m / T);
+      int ts = t + kk - 1;
+      ts = ts < 0 ? ts + T : (ts >= T ? ts - T : ts);
+      v = ld_as_f32<TIn>(x + (size_t(b) * T + ts) * C + c);
+    }
+    rows[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace mt
+
+extern "C" int mt_im2row1d_circular(const void* x, int x_dtype, void* rows, int B, int T, int C, int Kp, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && rows, MT_ERR_BAD_SHAPE, "mt_im2row1d_circular: null pointer");
+  MT_REQUIRE(B > 0 && T > 0 && C > 0 && Kp >= 3 * C && Kp % 8 == 0, MT_ERR_BAD_SHAPE,
+             "mt_im2row1d_circular: need B,T,C > 0 and Kp >= 3*C with Kp %% 8 == 0");
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const long long total = (long long)B * T * Kp;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sms * 32) blocks = (long long)sms * 32;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (x_dtype == MT_DT_F32)
+    im2row1d_circular_kernel<float><<<unsigned(blocks), 256, 0, s>>>(reinterpret_cast<const float*>(x),
+                                                                     reinterpret_cast<__nv_bfloat16*>(rows), B, T, C, Kp);
+  else if (x_dtype == MT_DT_BF16)
+    im2row1d_circular_kernel<__nv_bfloat16><<<unsigned(blocks), 256, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(rows), B, T, C, Kp);
+  else {
+    set_error("mt_im2row1d_circular: x_dtype must be fp32 or bf16 (got %d)", x_dtype);
+    return MT_ERR_BAD_DTYPE;
+  }
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
 
 extern "C" int mt_im2row(const void* x, int x_dtype, void* rows, int B, int C, int T, int H, int W, int kt, int kh,
                          int kw, int st, int sh, int sw, void* stream) {

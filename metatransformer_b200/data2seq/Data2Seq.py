@@ -8,14 +8,16 @@ are kept and the *intended* semantics implemented:
   audio                    : the reference has no `embed` for audio and returns a raw fbank (Data2Seq.py:38-45,53-54);
                              here a (B, T, F) fbank is tokenised like AST (ast_models.py:86,152-155) with
                              Acoustic.PatchEmbed(embed_dim=dim, fstride=10, tstride=10)
-  time-series / imu, text, graph, hyper : not built yet -> NotImplementedError
+  time-series / imu        : Time_Series.DataEmbedding(c_in=1, d_model=dim)                  (Data2Seq.py:35-36, with the
+                             `cin=` typo fixed)
+  text, graph, hyper       : not built yet -> NotImplementedError
 """
 import torch.nn as nn
 
-from . import Acoustic, Image, Video
+from . import Acoustic, Image, Time_Series, Video
 
 _IMAGE_LIKE = ('image', 'infrared', 'x-ray')
-_NEXT = ('text', 'graph', 'hyper', 'time-series', 'imu')
+_NEXT = ('text', 'graph', 'hyper')
 
 
 class Data2Seq(nn.Module):
@@ -30,6 +32,8 @@ class Data2Seq(nn.Module):
             self.embed = Video.PatchEmbed(embed_dim=self.embed_dim, token_dtype=token_dtype)
         elif self.modality == 'audio':
             self.embed = Acoustic.PatchEmbed(embed_dim=self.embed_dim, fstride=10, tstride=10, token_dtype=token_dtype)
+        elif self.modality in ('time-series', 'imu'):
+            self.embed = Time_Series.DataEmbedding(c_in=1, d_model=self.embed_dim, token_dtype=token_dtype)
         elif self.modality in _NEXT:
             raise NotImplementedError(f"Data2Seq modality '{modality}' is not built on the B200 path yet "
                                       "(SURVEY.md §8f rank 3)")

@@ -249,6 +249,18 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return linear(dyt, xt)
 
 
+def im2row1d_circular(x: torch.Tensor) -> torch.Tensor:
+    """x [B,T,C] (fp32/bf16) -> rows [B*T, Kp] bf16 for the circular k=3 Conv1d token embedding (Kp = 3C rounded up to 8)."""
+    _require_cuda(x)
+    B, T, C = x.shape
+    Kp = (3 * C + 7) // 8 * 8
+    rows = torch.empty((B * T, Kp), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_im2row1d_circular(x.data_ptr(), _DT[x.dtype], rows.data_ptr(), B, T, C, Kp, _stream()),
+              "mt_im2row1d_circular")
+    return rows
+
+
 def im2row(x: torch.Tensor, kernel: Sequence[int], stride: Sequence[int]) -> Tuple[torch.Tensor, Tuple[int, int, int]]:
     """x [B,C,T,H,W] (fp32/bf16) -> rows [B*Tp*Hp*Wp, C*kt*kh*kw] bf16 and (Tp,Hp,Wp)."""
     _require_cuda(x)

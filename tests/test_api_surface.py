@@ -76,6 +76,8 @@ def test_data2seq_surface():
     assert v.proj.weight.shape == (1024, 3, 2, 16, 16) and v.num_patches == 1568
     a = mt.Data2Seq("audio", 768).embed
     assert a.proj.weight.shape == (768, 1, 16, 16) and a.proj.stride == (10, 10)
+    ts = mt.Data2Seq("imu", 768).embed
+    assert ts.value_embedding.tokenConv.weight.shape == (768, 1, 3) and ts.position_embedding.pe.shape == (1, 5000, 768)
 
 
 def test_compat_shim_resolves_reference_imports():

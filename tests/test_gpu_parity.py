@@ -297,3 +297,18 @@ def test_pipeline_image_to_tokens_to_encoder(mt):
     ref = orc.encoder(t_ref, sd, 2, 12)
     _assert_close(t, t_ref, what="tokens")
     _assert_close(y, ref, what="image -> tokens -> encoder")
+
+
+def test_time_series_tokenizer_matches_reference_golden(mt, golden_dir):
+    """Data2Seq/Time_Series.py DataEmbedding (circular Conv1d k=3 + sinusoid PE) vs the reference-generated golden."""
+    z = np.load(golden_dir / "time_series_embed.npz")
+    emb = mt.data2seq.Time_Series.DataEmbedding(c_in=7, d_model=64)
+    emb.value_embedding.tokenConv.weight.data.copy_(torch.from_numpy(z["w"]))
+    emb = emb.cuda().eval()
+    with torch.no_grad():
+        y = emb(torch.from_numpy(z["x"]).cuda())
+    assert y.shape == (3, 96, 64) and y.dtype == torch.float32
+    _assert_close(y, torch.from_numpy(z["y"]), what="time-series DataEmbedding golden")
+    t = mt.Data2Seq("time-series", 768).cuda().eval()
+    with torch.no_grad():
+        assert t(torch.randn(2, 96, 1, device="cuda")).shape == (2, 96, 768)
