@@ -125,6 +125,10 @@ int mt_im2row(const void* x, int x_dtype, void* rows, int B, int C, int T, int H
  * The sinusoid positional embedding (Time_Series.py:8-26) is added by the GEMM's residual input.               */
 int mt_im2row1d_circular(const void* x, int x_dtype, void* rows, int B, int T, int C, int Kp, void* stream);
 
+/* ---- hyperspectral tokenizer helper: out[b,0,:] = first, out[b,1+i,:] = tok[b,i,:] (cls-token concat,
+ * Hyper-spectrum/metatransformer.py:155-157); bf16, d % 8 == 0 ---- */
+int mt_prepend_row(const void* tok, const void* first, void* out, int B, int n, int d, void* stream);
+
 /* ---- dtype conversion helper (weights packing, fp32 activations at the boundary) ---- */
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 

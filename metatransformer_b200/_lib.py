@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_gemm_bf16_ln", "mt_gemm_bf16_ex", "mt_row_stats",
     "mt_fold_layernorm", "mt_layernorm", "mt_layernorm_bwd", "mt_gelu", "mt_transpose_bf16", "mt_colsum", "mt_attention_fwd",
     "mt_attention_fwd_lse", "mt_attention_bwd_workspace_bytes", "mt_attention_bwd",
-    "mt_im2row", "mt_im2row1d_circular", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
+    "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
     "mt_encoder_forward", "mt_encoder_launches_per_forward",
 )
 
@@ -94,6 +94,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_im2row.argtypes = [c_void_p, c_int, c_void_p] + [c_int] * 11 + [c_void_p]
     lib.mt_im2row1d_circular.restype = c_int
     lib.mt_im2row1d_circular.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mt_prepend_row.restype = c_int
+    lib.mt_prepend_row.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mt_cast.restype = c_int
     lib.mt_cast.argtypes = [c_void_p, c_int, c_void_p, c_int, c_size_t, c_void_p]
     lib.mt_encoder_create.restype = c_int

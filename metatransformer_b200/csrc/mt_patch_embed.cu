@@ -130,7 +130,44 @@ __global__ void __launch_bounds__(256) im2row1d_circular_kernel(const TIn* __res
   }
 }
 
+// out[b, 0, :] = first[:], out[b, 1 + i, :] = tok[b, i, :]  — prepends a (cls + pos) row to every sequence
+// (Hyper-spectrum/metatransformer.py:155-157: cat(cls_tokens, x) on the token axis).  16-byte vectors.
+__global__ void __launch_bounds__(256) prepend_row_kernel(const __nv_bfloat16* __restrict__ tok,
+                                                           const __nv_bfloat16* __restrict__ first,
+                                                           __nv_bfloat16* __restrict__ out, int B, int n, int d8) {
+  const long long total = (long long)B * (n + 1) * d8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = int(idx % d8);
+    const long long r = idx / d8;
+    const int i = int(r % (n + 1));
+    const long long b = r / (n + 1);
+    const uint4 v = (i == 0) ? reinterpret_cast<const uint4*>(first)[c]
+                             : reinterpret_cast<const uint4*>(tok)[(b * n + (i - 1)) * d8 + c];
+    reinterpret_cast<uint4*>(out)[idx] = v;
+  }
+}
+
 }  // namespace mt
+
+extern "C" int mt_prepend_row(const void* tok, const void* first, void* out, int B, int n, int d, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(tok && first && out, MT_ERR_BAD_SHAPE, "mt_prepend_row: null pointer");
+  MT_REQUIRE(B > 0 && n > 0 && d > 0 && d % 8 == 0, MT_ERR_BAD_SHAPE, "mt_prepend_row: need B, n > 0 and d %% 8 == 0");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(tok) | reinterpret_cast<uintptr_t>(first) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_prepend_row: pointers must be 16-byte aligned");
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const long long total = (long long)B * (n + 1) * (d / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sms * 32) blocks = (long long)sms * 32;
+  prepend_row_kernel<<<unsigned(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(tok), reinterpret_cast<const __nv_bfloat16*>(first),
+      reinterpret_cast<__nv_bfloat16*>(out), B, n, d / 8);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
 
 extern "C" int mt_im2row1d_circular(const void* x, int x_dtype, void* rows, int B, int T, int C, int Kp, void* stream) {
   using namespace mt;

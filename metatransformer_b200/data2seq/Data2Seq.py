@@ -10,14 +10,16 @@ are kept and the *intended* semantics implemented:
                              Acoustic.PatchEmbed(embed_dim=dim, fstride=10, tstride=10)
   time-series / imu        : Time_Series.DataEmbedding(c_in=1, d_model=dim)                  (Data2Seq.py:35-36, with the
                              `cin=` typo fixed)
-  text, graph, hyper       : not built yet -> NotImplementedError
+  hyper                    : Hyper_Spectrum.PatchEmbed(embed_dim=dim): Linear + cls + pos (Data2Seq.py:33-34; working
+                             form Hyper-spectrum/metatransformer.py:152-159)
+  text, graph              : not built yet -> NotImplementedError
 """
 import torch.nn as nn
 
-from . import Acoustic, Image, Time_Series, Video
+from . import Acoustic, Hyper_Spectrum, Image, Time_Series, Video
 
 _IMAGE_LIKE = ('image', 'infrared', 'x-ray')
-_NEXT = ('text', 'graph', 'hyper')
+_NEXT = ('text', 'graph')
 
 
 class Data2Seq(nn.Module):
@@ -32,6 +34,8 @@ class Data2Seq(nn.Module):
             self.embed = Video.PatchEmbed(embed_dim=self.embed_dim, token_dtype=token_dtype)
         elif self.modality == 'audio':
             self.embed = Acoustic.PatchEmbed(embed_dim=self.embed_dim, fstride=10, tstride=10, token_dtype=token_dtype)
+        elif self.modality == 'hyper':
+            self.embed = Hyper_Spectrum.PatchEmbed(embed_dim=self.embed_dim, token_dtype=token_dtype)
         elif self.modality in ('time-series', 'imu'):
             self.embed = Time_Series.DataEmbedding(c_in=1, d_model=self.embed_dim, token_dtype=token_dtype)
         elif self.modality in _NEXT:

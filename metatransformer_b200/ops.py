@@ -261,6 +261,17 @@ def im2row1d_circular(x: torch.Tensor) -> torch.Tensor:
     return rows
 
 
+def prepend_row(tok: torch.Tensor, first: torch.Tensor) -> torch.Tensor:
+    """tok [B,n,d] bf16, first [d] bf16 -> [B,n+1,d] with `first` as token 0 of every sequence."""
+    _require_cuda(tok, first)
+    B, n, d = tok.shape
+    out = torch.empty((B, n + 1, d), dtype=torch.bfloat16, device=tok.device)
+    with torch.cuda.device(tok.device):
+        check(_lib.load().mt_prepend_row(tok.data_ptr(), first.data_ptr(), out.data_ptr(), B, n, d, _stream()),
+              "mt_prepend_row")
+    return out
+
+
 def im2row(x: torch.Tensor, kernel: Sequence[int], stride: Sequence[int]) -> Tuple[torch.Tensor, Tuple[int, int, int]]:
     """x [B,C,T,H,W] (fp32/bf16) -> rows [B*Tp*Hp*Wp, C*kt*kh*kw] bf16 and (Tp,Hp,Wp)."""
     _require_cuda(x)

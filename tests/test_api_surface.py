@@ -61,6 +61,8 @@ def test_unsupported_configurations_raise():
         mt.Block(64, 1, norm_layer=nn.BatchNorm1d)
     with pytest.raises(NotImplementedError):
         mt.Data2Seq("graph", 768)
+    with pytest.raises(NotImplementedError):
+        mt.Data2Seq("text", 768)
     with pytest.raises(ValueError):
         mt.Data2Seq("smell", 768)
 
@@ -76,6 +78,8 @@ def test_data2seq_surface():
     assert v.proj.weight.shape == (1024, 3, 2, 16, 16) and v.num_patches == 1568
     a = mt.Data2Seq("audio", 768).embed
     assert a.proj.weight.shape == (768, 1, 16, 16) and a.proj.stride == (10, 10)
+    hy = mt.Data2Seq("hyper", 768).embed
+    assert hy.patch_to_embedding.weight.shape == (768, 224 * 224) and hy.pos_embedding.shape == (1, 17, 768)
     ts = mt.Data2Seq("imu", 768).embed
     assert ts.value_embedding.tokenConv.weight.shape == (768, 1, 3) and ts.position_embedding.pe.shape == (1, 5000, 768)
 

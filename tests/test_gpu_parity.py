@@ -312,3 +312,18 @@ def test_time_series_tokenizer_matches_reference_golden(mt, golden_dir):
     t = mt.Data2Seq("time-series", 768).cuda().eval()
     with torch.no_grad():
         assert t(torch.randn(2, 96, 1, device="cuda")).shape == (2, 96, 768)
+
+
+def test_hyperspectral_tokenizer_matches_oracle(mt):
+    """Linear(patch_dim, d) -> [cls ; tokens] + pos (Hyper-spectrum/metatransformer.py:152-159) vs written-out fp64 math."""
+    emb = mt.data2seq.Hyper_Spectrum.PatchEmbed(near_band=1, img_size=8, patch_size=16, embed_dim=96).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 10, 64, generator=g)
+    w, b = emb.patch_to_embedding.weight.detach().cpu().double(), emb.patch_to_embedding.bias.detach().cpu().double()
+    tok = orc.linear(x.double(), w, b)
+    ref = torch.cat([emb.cls_token.detach().cpu().double().expand(3, 1, 96), tok], dim=1) + \
+        emb.pos_embedding.detach().cpu().double()[:, :11]
+    with torch.no_grad():
+        y = emb(x.cuda())
+    assert y.shape == (3, 11, 96)
+    _assert_close(y, ref, what="hyperspectral tokenizer")

@@ -241,7 +241,23 @@ def group_prof_fc2():
     torch.cuda.synchronize()
 
 
-GROUPS = {"prof": group_prof, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+def group_prof_layer():
+    """one Base-16 layer's worth of kernels at C2 size through the fused driver (for ncu --set full captures)"""
+    import torch
+    import metatransformer_b200 as mt
+    from oracle import encoder_oracle as orc
+    enc = mt.build_encoder("base", depth=2)
+    enc.load_state_dict(orc.make_encoder_state_dict(768, 2, seed=0), strict=True)
+    enc = enc.cuda().eval()
+    fused = mt.FusedEncoder(enc)
+    x = torch.randn(256, 196, 768).bfloat16().cuda()
+    with torch.no_grad():
+        for _ in range(2):
+            fused(x)
+    torch.cuda.synchronize()
+
+
+GROUPS = {"prof": group_prof, "prof_layer": group_prof_layer, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
 
 
 def main():
