@@ -297,13 +297,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(32 * q) << 16) + uint32_t(as * kBN + 128 * hf);
-      // One 32-column slice: accumulator registers -> bias / LN fold / GELU / residual -> bf16 -> staging -> TMA store.
-      auto process_slice = [&](const uint32_t (&acc)[32], const int sc) {
+#pragma unroll 1
+      for (int sc = 0; sc < 4; ++sc) {  // four 32-column slices; two slices = one 64-column TMA store
         const int c_sc = col0 + 32 * sc;
         uint4 rv[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) rv[j] = rv_next[j];
         if (sc < 3) load_resid(sc + 1, rv_next);
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(t_row + uint32_t(32 * sc), acc);
+        tmem_wait_ld();
+        if (sc == 3) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_remote(tempty_bar(as), 0);
+            else mbar_arrive(tempty_bar(as));
+          }
+        }
         if ((sc & 1) == 0 && store_pending) {
           // staging buffer is about to be overwritten: previous TMA store must have read it
           if (lane == 0) tma_store_wait_read<0>();
@@ -364,31 +376,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           store_pending = true;
         }
-      };
-      // TMEM loads are software-pipelined: the load of slice sc+1 is in flight while slice sc is being processed
-      // (with two epilogue warps per SM sub-partition the tcgen05.ld latency would otherwise be exposed every slice)
-      uint32_t acc_a[32], acc_b[32];
-      tmem_ld_32x32b_x32(t_row, acc_a);
-      tmem_wait_ld();
-      tmem_ld_32x32b_x32(t_row + 32u, acc_b);
-      process_slice(acc_a, 0);
-      tmem_wait_ld();
-      tmem_ld_32x32b_x32(t_row + 64u, acc_a);
-      process_slice(acc_b, 1);
-      tmem_wait_ld();
-      tmem_ld_32x32b_x32(t_row + 96u, acc_b);
-      process_slice(acc_a, 2);
-      tmem_wait_ld();
-      {
-        // all TMEM reads of this accumulator stage are done: hand it back to the MMA issuer
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_remote(tempty_bar(as), 0);
-          else mbar_arrive(tempty_bar(as));
-        }
       }
-      process_slice(acc_b, 3);
       if (p.out_row_sums != nullptr && row < p.M) {
         float a0, a1, q0, q1;
         unpack_f32x2(rs2, a0, a1);
