@@ -95,11 +95,15 @@ int mt_gelu(const void* u, void* h, size_t n, void* stream);
  * (mt_transpose_bf16: dst[C, ldd] = src[R, C]^T, zero-padded to ldd >= R), db = column sums of dY (fp32).  */
 int mt_transpose_bf16(const void* src, void* dst, int R, int C, int ldd, void* stream);
 int mt_colsum(const void* x, float* out, int M, int N, void* stream);
+/* weight gradients of a LayerNorm-folded Linear (fine-tune mode): from dWf = dY^T xhat (bf16 [N,K]) and dyb = colsum(dY):
+ * dW = dWf*gamma + dyb (x) beta, dgamma = sum_n dWf*W, dbeta = sum_n dyb*W (fp32 outputs).                      */
+int mt_ln_fold_bwd(const void* dw_folded, const void* w, int w_dtype, const float* gamma, const float* beta,
+                   const float* dyb, float* dw, float* dgamma, float* dbeta, int N, int K, void* stream);
 
 /* ---- E4: softmax attention core -----------------------------------------------------------------------------
  * qkv: bf16 [B, N, 3, H, dh] (the packed output of the qkv Linear, attention.py:28), out: bf16 [B, N, H*dh].
  * out[b,n,h,:] = softmax_j(scale * q[b,n,h]·k[b,j,h]) · v[b,j,h]   (attention.py:31-35, no mask, no dropout).
- * dh must be 64.                                                                                             */
+ * dh = 64: tcgen05 kernel (both published encoders); dh in {8,16,...,56}: generic SIMT kernel (e.g. Graph: 24). */
 int mt_attention_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, void* stream);
 
 /* Same, additionally writing lse2[B,H,N] = log2-sum-exp of the scaled scores (needed by mt_attention_bwd). */

@@ -17,7 +17,7 @@ MT_DT_BF16, MT_DT_F32, MT_DT_F16 = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
     "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_gemm_bf16_ln", "mt_gemm_bf16_ex", "mt_row_stats",
-    "mt_fold_layernorm", "mt_layernorm", "mt_layernorm_bwd", "mt_gelu", "mt_transpose_bf16", "mt_colsum", "mt_attention_fwd",
+    "mt_fold_layernorm", "mt_layernorm", "mt_layernorm_bwd", "mt_gelu", "mt_transpose_bf16", "mt_colsum", "mt_ln_fold_bwd", "mt_attention_fwd",
     "mt_attention_fwd_lse", "mt_attention_bwd_workspace_bytes", "mt_attention_bwd",
     "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
     "mt_encoder_forward", "mt_encoder_launches_per_forward",
@@ -82,6 +82,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_transpose_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.mt_colsum.restype = c_int
     lib.mt_colsum.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.mt_ln_fold_bwd.restype = c_int
+    lib.mt_ln_fold_bwd.argtypes = [c_void_p, c_void_p, c_int] + [c_void_p] * 6 + [c_int, c_int, c_void_p]
     lib.mt_attention_fwd.restype = c_int
     lib.mt_attention_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]
     lib.mt_attention_fwd_lse.restype = c_int

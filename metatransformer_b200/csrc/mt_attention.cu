@@ -408,10 +408,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
 }  // namespace mt
 
+namespace mt {
+int attention_generic_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, cudaStream_t s);
+}
+
 static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale,
                               void* stream) {
   using namespace mt;
   MT_REQUIRE(qkv && out, MT_ERR_BAD_SHAPE, "mt_attention_fwd: null pointer");
+  if (dh != 64 && lse2 == nullptr && B > 0 && N > 0 && H > 0 && scale > 0.f &&
+      ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    return attention_generic_fwd(qkv, out, B, N, H, dh, scale, reinterpret_cast<cudaStream_t>(stream));
   MT_REQUIRE(B > 0 && N > 0 && H > 0, MT_ERR_BAD_SHAPE, "mt_attention_fwd: B, N, H must be positive");
   MT_REQUIRE(dh == 64, MT_ERR_UNSUPPORTED, "mt_attention_fwd: head_dim %d not supported (only 64)", dh);
   MT_REQUIRE(scale > 0.f, MT_ERR_UNSUPPORTED, "mt_attention_fwd: scale must be positive");

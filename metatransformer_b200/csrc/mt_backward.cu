@@ -125,7 +125,63 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   atomicAdd(out + col, s);
 }
 
+// Un-folding of the weight gradient of a LayerNorm-folded Linear (forward: y = xhat W'^T + b', W' = W*gamma, b' = b + W beta):
+//   dW[n,k]   = dWf[n,k] * gamma[k] + dyb[n] * beta[k]        (dWf = dY^T xhat, dyb = column sums of dY = db)
+//   dgamma[k] = sum_n dWf[n,k] * W[n,k]
+//   dbeta[k]  = sum_n dyb[n]   * W[n,k]
+// Threads run along k (coalesced), blocks split n; dgamma / dbeta are accumulated with fp32 atomics (zero-initialised).
+template <typename TW>
+__global__ void __launch_bounds__(256)
+ln_fold_bwd_kernel(const __nv_bfloat16* __restrict__ dwf, const TW* __restrict__ w, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ dyb, float* __restrict__ dw,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int K, int rows_per_block) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  const int n0 = blockIdx.y * rows_per_block;
+  const int n1 = min(N, n0 + rows_per_block);
+  const float g = gamma[k], bt = beta[k];
+  float sg = 0.f, sb = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    const float d = __bfloat162float(dwf[size_t(n) * K + k]);
+    float wv;
+    if constexpr (sizeof(TW) == 4) wv = w[size_t(n) * K + k];
+    else wv = __bfloat162float(w[size_t(n) * K + k]);
+    const float yb = dyb[n];
+    dw[size_t(n) * K + k] = fmaf(d, g, yb * bt);
+    sg = fmaf(d, wv, sg);
+    sb = fmaf(yb, wv, sb);
+  }
+  atomicAdd(dgamma + k, sg);
+  atomicAdd(dbeta + k, sb);
+}
+
 }  // namespace mt
+
+extern "C" int mt_ln_fold_bwd(const void* dw_folded, const void* w, int w_dtype, const float* gamma, const float* beta,
+                              const float* dyb, float* dw, float* dgamma, float* dbeta, int N, int K, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(dw_folded && w && gamma && beta && dyb && dw && dgamma && dbeta, MT_ERR_BAD_SHAPE, "mt_ln_fold_bwd: null pointer");
+  MT_REQUIRE(N > 0 && K > 0, MT_ERR_BAD_SHAPE, "mt_ln_fold_bwd: N and K must be positive");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MT_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, size_t(K) * 4, s));
+  MT_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, size_t(K) * 4, s));
+  const int rpb = 32;
+  dim3 grid(unsigned(ceil_div(K, 256)), unsigned(ceil_div(N, rpb)));
+  if (w_dtype == MT_DT_F32)
+    ln_fold_bwd_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dw_folded),
+                                                   reinterpret_cast<const float*>(w), gamma, beta, dyb, dw, dgamma, dbeta,
+                                                   N, K, rpb);
+  else if (w_dtype == MT_DT_BF16)
+    ln_fold_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dw_folded),
+                                                           reinterpret_cast<const __nv_bfloat16*>(w), gamma, beta, dyb, dw,
+                                                           dgamma, dbeta, N, K, rpb);
+  else {
+    set_error("mt_ln_fold_bwd: w_dtype must be fp32 or bf16 (got %d)", w_dtype);
+    return MT_ERR_BAD_DTYPE;
+  }
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
 
 extern "C" int mt_transpose_bf16(const void* src, void* dst, int R, int C, int ldd, void* stream) {
   using namespace mt;

@@ -243,6 +243,22 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def ln_fold_bwd(dw_folded: torch.Tensor, weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dyb: torch.Tensor):
+    """(dW fp32 [N,K], dgamma fp32 [K], dbeta fp32 [K]) of a LayerNorm-folded Linear from dWf = dY^T xhat and dyb = colsum(dY)."""
+    _require_cuda(dw_folded, weight, gamma, beta, dyb)
+    if weight.dtype not in (torch.float32, torch.bfloat16):
+        weight = weight.float()
+    N, K = weight.shape
+    dw = torch.empty((N, K), dtype=torch.float32, device=weight.device)
+    dg = torch.empty(K, dtype=torch.float32, device=weight.device)
+    db = torch.empty(K, dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        check(_lib.load().mt_ln_fold_bwd(dw_folded.data_ptr(), weight.data_ptr(), _DT[weight.dtype], gamma.data_ptr(),
+                                         beta.data_ptr(), dyb.data_ptr(), dw.data_ptr(), dg.data_ptr(), db.data_ptr(), N, K,
+                                         _stream()), "mt_ln_fold_bwd")
+    return dw, dg, db
+
+
 def linear_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """dW [N,K] = dy[M,N]^T @ x[M,K] (bf16 in, fp32 accumulate over M, bf16 out) via transposed copies + the TN GEMM."""
     dyt, xt = transpose(dy), transpose(x)          # [N, Mp], [K, Mp]

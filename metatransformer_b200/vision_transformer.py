@@ -262,7 +262,51 @@ class Block(nn.Module):
         dqkv = ops.attention_bwd(qkv.view(B, N, -1), o, do.view(B, N, -1), lse2, attn.num_heads, attn.scale)
         wqf = self._folded("fold.qkv", attn.qkv, self.norm1)[0]
         dxh1 = ops.linear(dqkv.view(M, -1), self._transposed("t.qkvf", wqf))
-        return ops.layernorm_bwd(dxh1, x2, stats1, None, add=g1)
+        dx = ops.layernorm_bwd(dxh1, x2, stats1, None, add=g1)
+        return dx, (g2, du, g1, dqkv.view(M, -1))
+
+    _PARAM_ORDER = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
+                    "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",
+                    "mlp.fc2.bias")
+
+    def _param_list(self):
+        named = dict(self.named_parameters())
+        return [named.get(k) for k in self._PARAM_ORDER]
+
+    def _weight_grads(self, saved, grads):
+        """Fine-tune mode: gradients of all 12 parameters, in `_PARAM_ORDER`.
+        Every Linear's dW = dY^T X runs as the TN GEMM on transposed copies (fp32 accumulation over the tokens, bf16
+        result); the two LayerNorm-folded Linears are un-folded by mt_ln_fold_bwd."""
+        x2, stats1, qkv, o, lse2, x_mid, stats2, u = saved
+        g2, du, g1, dqkv = grads
+        attn, mlp = self.attn, self.mlp
+        d = x2.shape[1]
+        cache = self.__dict__.setdefault("_mt_pack_cache", {})
+        if "ones" not in cache or cache["ones"][0].device != x2.device or cache["ones"][0].numel() != d:
+            cache["ones"] = (torch.ones(d, device=x2.device), torch.zeros(d, device=x2.device))
+        ones, zeros = cache["ones"]
+        f32 = lambda p_: _packed(self, "f32." + str(id(p_)), p_, torch.float32)  # noqa: E731
+        # --- mlp.fc2: input gelu(u) ---
+        hid = ops.gelu(u)
+        dw2 = ops.linear_wgrad(g2, hid)
+        db2 = ops.colsum(g2)
+        del hid
+        # --- mlp.fc1 (norm2 folded): input xhat2 ---
+        xh = ops.layernorm(x_mid, ones, zeros, self.norm2.eps)
+        dwf = ops.linear_wgrad(du, xh)
+        dyb1 = ops.colsum(du)
+        dw1, dg2, dbt2 = ops.ln_fold_bwd(dwf, mlp.fc1.weight.detach().contiguous(), f32(self.norm2.weight),
+                                         f32(self.norm2.bias), dyb1)
+        # --- attn.proj: input o ---
+        dwp = ops.linear_wgrad(g1, o.view(o.shape[0] * o.shape[1], -1))
+        dbp = ops.colsum(g1)
+        # --- attn.qkv (norm1 folded): input xhat1 ---
+        xh = ops.layernorm(x2, ones, zeros, self.norm1.eps, out=xh)
+        dwf = ops.linear_wgrad(dqkv, xh)
+        dybq = ops.colsum(dqkv)
+        dwq, dg1, dbt1 = ops.ln_fold_bwd(dwf, attn.qkv.weight.detach().contiguous(), f32(self.norm1.weight),
+                                         f32(self.norm1.bias), dybq)
+        return [dg1, dbt1, dwq, dybq if attn.qkv.bias is not None else None, dwp, dbp, dg2, dbt2, dw1, dyb1, dw2, db2]
 
     def forward(self, x):
         _check_input(x, "Block")
@@ -270,12 +314,8 @@ class Block(nn.Module):
         self.mlp._check_train()
         if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
             raise NotImplementedError("Block: drop_path > 0 in training mode is not implemented on the B200 path yet")
-        if torch.is_grad_enabled() and x.requires_grad:
-            if any(p.requires_grad for p in self.parameters()):
-                raise NotImplementedError("Block: weight gradients (fine-tuning the encoder, SURVEY.md §8f rank 1) are "
-                                          "not implemented yet; freeze the encoder (requires_grad_(False)) — the "
-                                          "input gradient for trainable tokenizers is supported")
-            return _BlockFn.apply(x, self)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return _BlockFn.apply(x, self, *[p for p in self._param_list() if p is not None])
         B, N, C = x.shape
         return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N), x)
 
@@ -284,17 +324,28 @@ class _BlockFn(torch.autograd.Function):
     """Autograd node of one frozen Block: forward and input-gradient both run on the sm_100a kernels."""
 
     @staticmethod
-    def forward(ctx, x, block):
+    def forward(ctx, x, block, *params):
         B, N, C = x.shape
         out2, saved = block._forward_train(_to_bf16_2d(x.detach()), B, N)
         ctx.block, ctx.saved, ctx.shape, ctx.in_dtype = block, saved, (B, N, C), x.dtype
+        ctx.params = params
         return _from_bf16(out2, x)
 
     @staticmethod
     def backward(ctx, g):
         B, N, C = ctx.shape
         g2 = _to_bf16_2d(g)
-        dx2 = ctx.block._backward_2d(g2, ctx.saved, B, N)
+        dx2, inter = ctx.block._backward_2d(g2, ctx.saved, B, N)
+        pgrads = [None] * len(ctx.params)
+        if any(ctx.needs_input_grad[2:]):
+            full = ctx.block._weight_grads(ctx.saved, inter)
+            present = [gr for gr, prm in zip(full, ctx.block._param_list()) if prm is not None]
+            for i, (gr, prm) in enumerate(zip(present, ctx.params)):
+                if ctx.needs_input_grad[2 + i] and gr is not None:
+                    gr = gr.view(prm.shape)
+                    pgrads[i] = gr if gr.dtype == prm.dtype else ops.cast(gr.contiguous(), prm.dtype)
         ctx.saved = None
-        dx = dx2 if ctx.in_dtype == torch.bfloat16 else ops.cast(dx2, ctx.in_dtype)
-        return dx.view(B, N, C), None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = (dx2 if ctx.in_dtype == torch.bfloat16 else ops.cast(dx2, ctx.in_dtype)).view(B, N, C)
+        return (dx, None, *pgrads)

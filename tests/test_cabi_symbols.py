@@ -48,7 +48,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mt_gemm_bf16(p, p, None, None, p, 128, 256, 64, 7, 0, None) == -4         # unknown activation
     assert lib.mt_layernorm(p, 0, p, p, p, 4, 12, 1e-5, None) == -1                       # d % 8
     assert lib.mt_layernorm(p, 5, p, p, p, 4, 16, 1e-5, None) == -2                       # dtype
-    assert lib.mt_attention_fwd(p, p, 1, 16, 2, 24, 0.2, None) == -4                      # head_dim 24 unsupported
+    assert lib.mt_attention_fwd(p, p, 1, 16, 2, 72, 0.2, None) == -4                      # head_dim 72 unsupported
     assert b"head_dim" in lib.mt_last_error()
     assert lib.mt_im2row(p, 1, p, 1, 3, 1, 8, 8, 1, 16, 16, 1, 16, 16, None) == -1        # kernel > input
     assert lib.mt_cast(p, 1, p, 9, 16, None) == -2

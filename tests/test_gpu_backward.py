@@ -78,10 +78,30 @@ def test_block_input_gradient_matches_oracle_autograd(mt):
     y.backward(gy.cuda().bfloat16())
     assert xg.grad is not None and xg.grad.dtype == torch.bfloat16
     _assert_close(xg.grad, xr.grad, rel=2e-2, mx=2e-2, what="dL/dx through 2 frozen Blocks")
-    # unfrozen encoder: weight gradients are not built yet -> loud error, no silent wrong training
-    enc.requires_grad_(True)
-    with pytest.raises(NotImplementedError, match="weight gradients"):
-        enc(xg)
+
+
+def test_finetune_weight_gradients_match_oracle_autograd(mt):
+    """Fine-tune mode: gradients of all 12 parameters of a Block vs fp64 autograd of the oracle."""
+    dim, heads = 768, 12
+    sd = orc.make_encoder_state_dict(dim, 1, seed=8)
+    sd = {k: (_bf16_round(v) if v.dim() == 2 else v) for k, v in sd.items()}
+    enc = mt.build_encoder("base", depth=1)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda().train()
+    g = torch.Generator().manual_seed(77)
+    x = _bf16_round(torch.randn(4, 196, dim, generator=g))
+    gy = _bf16_round(torch.randn(4, 196, dim, generator=g) * 0.05)
+    ref_p = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    orc.encoder(x.double(), ref_p, 1, heads).backward(gy.double())
+    y = enc(x.cuda().bfloat16())             # input does not require grad; parameters do
+    y.backward(gy.cuda().bfloat16())
+    for name, prm in enc.named_parameters():
+        assert prm.grad is not None, name
+        ref = ref_p[name].grad
+        tol = 3e-2
+        got = prm.grad.reshape(ref.shape)
+        rel = float((got.double().cpu() - ref).norm() / ref.norm().clamp_min(1e-12))
+        assert rel <= tol, f"{name}: rel_l2 {rel:.3e}"
 
 
 def test_transpose_and_colsum(mt):

@@ -22,7 +22,9 @@ def main():
     rank, local_rank, world = init_process_group("nccl")
     dev = torch.device("cuda", local_rank)
     torch.manual_seed(0)                                  # identical weights on every rank
-    enc = mt.build_encoder("base", depth=2).to(dev).eval().requires_grad_(False)
+    finetune = "--finetune" in sys.argv      # encoder weights trainable too: 2 x 7.1 M parameters -> several buckets
+    enc = mt.build_encoder("base", depth=2).to(dev)
+    enc = enc.train() if finetune else enc.eval().requires_grad_(False)
     tok = mt.Data2Seq("image", 768).to(dev)
     global_batch = 8
     g = torch.Generator().manual_seed(123)
@@ -31,7 +33,7 @@ def main():
     y = enc(tok(images[lo:hi].to(dev)))
     loss = y.float().square().mean() * (hi - lo) / global_batch * world   # so that the rank-mean equals the global mean
     loss.backward()
-    params = [p for p in tok.parameters() if p.requires_grad]
+    params = [p for p in list(tok.parameters()) + list(enc.parameters()) if p.requires_grad]
     local = [p.grad.clone() for p in params]
     n_coll = allreduce_gradients(params, world)
     # independent check: gather every rank's local gradients and average them
@@ -44,7 +46,8 @@ def main():
             bucket = [lg]
         mean = torch.stack(bucket).mean(0)
         ok &= bool(torch.allclose(p.grad, mean, rtol=1e-4, atol=1e-6))
-    print(f"rank {rank}/{world}: shard [{lo},{hi}) loss {loss.item():.5f} collectives {n_coll} "
+    nbytes = sum(p.numel() * p.element_size() for p in params)
+    print(f"rank {rank}/{world}: finetune={finetune} grad bytes {nbytes / 1e6:.1f} MB shard [{lo},{hi}) loss {loss.item():.5f} collectives {n_coll} "
           f"grad_norm {params[0].grad.norm().item():.5f} allreduce_ok={ok}", flush=True)
     if world > 1:
         dist.barrier()
