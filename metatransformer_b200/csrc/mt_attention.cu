@@ -454,10 +454,15 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
   int rc = sm_count(&sms);
   if (rc) return rc;
   int grid = p.num_items < sms ? p.num_items : sms;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
-    attr_set = true;
+  {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (nn.DataParallel drives several from one process)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    MT_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   MT_CHECK_CUDA(launch_pdl(attention_fwd_kernel, dim3(unsigned(grid)), dim3(kAtThreads), size_t(kAtSmemBytes),
                            reinterpret_cast<cudaStream_t>(stream), 1u, tm_qkv, tm_out, p));

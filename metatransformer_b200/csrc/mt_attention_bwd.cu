@@ -392,10 +392,15 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
   int rc = sm_count(&sms);
   if (rc) return rc;
   const int grid = p.num_items < sms ? p.num_items : sms;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
-    attr_set = true;
+  {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (nn.DataParallel drives several from one process)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    MT_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   attention_bwd_kernel<<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, p);
   MT_CHECK_CUDA(cudaGetLastError());

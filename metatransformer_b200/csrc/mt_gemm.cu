@@ -450,10 +450,15 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   if (clusters < 1) clusters = 1;
 
   auto kern = gemm_bf16_kernel<CG>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+  {
+    // the opt-in to > 48 KB of dynamic shared memory is per device (nn.DataParallel drives several from one process)
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    MT_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      MT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   MT_CHECK_CUDA(launch_pdl(kern, dim3(unsigned(clusters * CG), 1, 1), dim3(kGemmThreads, 1, 1), size_t(Cfg::kSmemBytes),
                            stream, unsigned(CG), tm_a, tm_b, tm_y, p));
