@@ -77,6 +77,10 @@ typedef struct {
 } mt_gemm_opts;
 int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int N, int K, const mt_gemm_opts* opts, void* stream);
 
+/* Split-K form for weight gradients: y_f32[M,N] = x[M,K] @ w[N,K]^T in fp32, the K range split over `splits` CTA pairs
+ * per output tile (0 = auto) and reduced with fp32 atomics (y is zeroed inside).  dW = dY^T X with x = dY^T, w = X^T.  */
+int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, int M, int N, int K, int splits, void* stream);
+
 /* ---- E2: LayerNorm over the last dim, fp32 statistics, biased variance -------------------------------------
  * y[M,d] (bf16) = (x - mean) * rsqrt(var + eps) * gamma + beta;  x bf16 or fp32 (x_dtype), gamma/beta fp32.
  * Replaces norm1 / norm2 = nn.LayerNorm(d) of Block (attention.py:46,50; eps 1e-5 per README.md:131).       */
@@ -95,9 +99,9 @@ int mt_gelu(const void* u, void* h, size_t n, void* stream);
  * (mt_transpose_bf16: dst[C, ldd] = src[R, C]^T, zero-padded to ldd >= R), db = column sums of dY (fp32).  */
 int mt_transpose_bf16(const void* src, void* dst, int R, int C, int ldd, void* stream);
 int mt_colsum(const void* x, float* out, int M, int N, void* stream);
-/* weight gradients of a LayerNorm-folded Linear (fine-tune mode): from dWf = dY^T xhat (bf16 [N,K]) and dyb = colsum(dY):
- * dW = dWf*gamma + dyb (x) beta, dgamma = sum_n dWf*W, dbeta = sum_n dyb*W (fp32 outputs).                      */
-int mt_ln_fold_bwd(const void* dw_folded, const void* w, int w_dtype, const float* gamma, const float* beta,
+/* weight gradients of a LayerNorm-folded Linear (fine-tune mode): from dWf = dY^T xhat (fp32 [N,K]) and dyb = colsum(dY):
+ * dW = dWf*gamma + dyb (x) beta, dgamma = sum_n dWf*W, dbeta = sum_n dyb*W (fp32 in / out; dw may alias dw_folded). */
+int mt_ln_fold_bwd(const void* dw_folded /* fp32 [N,K] */, const void* w, int w_dtype, const float* gamma, const float* beta,
                    const float* dyb, float* dw, float* dgamma, float* dbeta, int N, int K, void* stream);
 
 /* ---- E4: softmax attention core -----------------------------------------------------------------------------

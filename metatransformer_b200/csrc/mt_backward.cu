@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 // Threads run along k (coalesced), blocks split n; dgamma / dbeta are accumulated with fp32 atomics (zero-initialised).
 template <typename TW>
 __global__ void __launch_bounds__(256)
-ln_fold_bwd_kernel(const __nv_bfloat16* __restrict__ dwf, const TW* __restrict__ w, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, const float* __restrict__ dyb, float* __restrict__ dw,
+ln_fold_bwd_kernel(const float* dwf, const TW* __restrict__ w, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ dyb, float* dw,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int K, int rows_per_block) {
   const int k = blockIdx.x * 256 + threadIdx.x;
   if (k >= K) return;
@@ -142,7 +142,7 @@ ln_fold_bwd_kernel(const __nv_bfloat16* __restrict__ dwf, const TW* __restrict__
   const float g = gamma[k], bt = beta[k];
   float sg = 0.f, sb = 0.f;
   for (int n = n0; n < n1; ++n) {
-    const float d = __bfloat162float(dwf[size_t(n) * K + k]);
+    const float d = dwf[size_t(n) * K + k];
     float wv;
     if constexpr (sizeof(TW) == 4) wv = w[size_t(n) * K + k];
     else wv = __bfloat162float(w[size_t(n) * K + k]);
@@ -168,11 +168,11 @@ extern "C" int mt_ln_fold_bwd(const void* dw_folded, const void* w, int w_dtype,
   const int rpb = 32;
   dim3 grid(unsigned(ceil_div(K, 256)), unsigned(ceil_div(N, rpb)));
   if (w_dtype == MT_DT_F32)
-    ln_fold_bwd_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dw_folded),
+    ln_fold_bwd_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dw_folded),
                                                    reinterpret_cast<const float*>(w), gamma, beta, dyb, dw, dgamma, dbeta,
                                                    N, K, rpb);
   else if (w_dtype == MT_DT_BF16)
-    ln_fold_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dw_folded),
+    ln_fold_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(dw_folded),
                                                            reinterpret_cast<const __nv_bfloat16*>(w), gamma, beta, dyb, dw,
                                                            dgamma, dbeta, N, K, rpb);
   else {

@@ -61,6 +61,11 @@ struct GemmParams {
   int ln_sums;                  // > 0: row_stats holds ln_sums partial (sum, sum of squares) pairs per row, written by
                                 // the epilogue of the GEMM that produced this GEMM's input
   float ln_eps;
+  // split-K accumulation mode (weight gradients: few output tiles, very long K): work item = (tile, K split); the
+  // epilogue adds the fp32 partial tile to out_f32 [M,N] with red.global.add (zero-initialised by the host wrapper)
+  float* out_f32;
+  int split_k;                  // >= 1
+  int kb_per_split;             // k-blocks per split (every split is non-empty)
   float* out_row_sums;          // [M][2*num_n_tiles][2]: per-(row, 128-column slice) partial (sum, sum of squares) of
                                 // this GEMM's output, or nullptr (plain stores: deterministic, no zero-init)
   const float* colsum;          // [N] sum_k W'[n,k] (of the bf16-rounded folded weight) or nullptr
@@ -166,7 +171,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   pdl_launch_dependents();
   pdl_wait();
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;   // work items: (tile, K split), split fastest
   const int num_kb = (p.K + kBK - 1) / kBK;
 
   if (warp == 0) {
@@ -176,10 +181,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       uint32_t phase = 0;
       const uint32_t full_leader_base = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m_tile = t / p.num_n_tiles, n_tile = t % p.num_n_tiles;
+        const int tile = t / p.split_k, split = t - tile * p.split_k;
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
         const int row_a = m_tile * (kBM * CG) + int(rank) * kBM;
         const int row_b = n_tile * kBN + ((CG == 2) ? int(rank) * (kBN / 2) : 0);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_begin = split * p.kb_per_split, kb_end = min(num_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
@@ -212,7 +219,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * kBN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = t % p.split_k;
+        const int kb_begin = split * p.kb_per_split, kb_end = min(num_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -222,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
             umma_f16_ss<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
-                            (kb > 0 || k > 0) ? 1u : 0u);
+                            (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           if constexpr (CG == 2) umma_commit_cg2_mc(empty_bar(stage), 0x3);
           else umma_commit(empty_bar(stage));
@@ -244,7 +253,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint32_t aphase = 0;
     bool store_pending = false;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int m_tile = t / p.num_n_tiles, n_tile = t % p.num_n_tiles;
+      const int tile = t / p.split_k;
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
       const int row0 = m_tile * (kBM * CG) + int(rank) * kBM + 32 * q;  // first row of this warp
       const int col0 = n_tile * kBN + 128 * hf;                          // first column of this warp
       const int row = row0 + lane;
@@ -315,6 +325,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if constexpr (CG == 2) mbar_arrive_remote(tempty_bar(as), 0);
             else mbar_arrive(tempty_bar(as));
           }
+        }
+        if (p.out_f32 != nullptr) {
+          // split-K accumulation: add this partial slice straight from registers (16-byte vector reductions)
+          if (row < p.M) {
+            float* dst = p.out_f32 + size_t(row) * p.N + c_sc;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              if (c_sc + e < p.N)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + e), "f"(__uint_as_float(acc[e])),
+                             "f"(__uint_as_float(acc[e + 1])), "f"(__uint_as_float(acc[e + 2])),
+                             "f"(__uint_as_float(acc[e + 3])) : "memory");
+            }
+          }
+          continue;
         }
         if ((sc & 1) == 0 && store_pending) {
           // staging buffer is about to be overwritten: previous TMA store must have read it
@@ -403,7 +427,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 template <int CG>
 static int launch_gemm(const void* x, const void* w, const float* bias, const void* resid, int ldr, void* y, int M,
                        int N, int K, int act, const float* row_stats, const float* colsum, int ln_sums, float ln_eps,
-                       float* out_row_sums, cudaStream_t stream) {
+                       float* out_row_sums, cudaStream_t stream, float* out_f32 = nullptr, int split_k = 1) {
   using Cfg = GemmCfg<CG>;
   CUtensorMap tm_a, tm_b, tm_y;
   {
@@ -421,10 +445,12 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {uint64_t(N), uint64_t(M)};
-    uint64_t strides[1] = {uint64_t(N) * 2};
+    // (in split-K mode the bf16 output map is unused; it is encoded over the X operand only to keep the launch uniform)
+    uint64_t dims[2] = {uint64_t(out_f32 ? K : N), uint64_t(M)};
+    uint64_t strides[1] = {uint64_t(out_f32 ? K : N) * 2};
     uint32_t box[2] = {64u, 32u};
-    int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_f32 ? x : y, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   GemmParams p;
@@ -438,13 +464,20 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   p.ln_sums = ln_sums;
   p.ln_eps = ln_eps;
   p.out_row_sums = out_row_sums;
+  p.out_f32 = out_f32;
+  {
+    const int num_kb = ceil_div(K, kBK);
+    int sk = split_k < 1 ? 1 : (split_k > num_kb ? num_kb : split_k);
+    p.kb_per_split = ceil_div(num_kb, sk);
+    p.split_k = ceil_div(num_kb, p.kb_per_split);   // every split non-empty
+  }
   p.num_m_tiles = ceil_div(M, kBM * CG);
   p.num_n_tiles = ceil_div(N, kBN);
 
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   int clusters = sms / CG;
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
@@ -529,4 +562,28 @@ extern "C" int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int
   }
   return gemm_entry("mt_gemm_bf16_ex", x, w, o->bias, o->residual, y, M, N, K, o->act, o->ln_row_stats, o->ln_colsum,
                     o->cta_group, stream, o->ln_stats_are_sums, o->ln_eps, o->out_row_sums);
+}
+
+// y_f32[M,N] += x[M,K] @ w[N,K]^T with the K range split over `splits` CTAs per output tile (fp32 atomics).
+// Meant for weight gradients dW = dY^T X (x = dY^T, w = X^T): a handful of output tiles and K = number of tokens.
+extern "C" int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, int M, int N, int K, int splits,
+                                   void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && w && y_f32, MT_ERR_BAD_SHAPE, "mt_gemm_bf16_splitk: null pointer");
+  MT_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 4 == 0, MT_ERR_BAD_SHAPE,
+             "mt_gemm_bf16_splitk: need M,N,K > 0, K %% 8 == 0, N %% 4 == 0 (got %d,%d,%d)", M, N, K);
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y_f32)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_gemm_bf16_splitk: pointers must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (splits <= 0) {
+    // auto: enough (tile, split) work items for two waves of CTA pairs
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
+    const int tiles = ceil_div(M, 2 * kBM) * ceil_div(N, kBN);
+    splits = ceil_div(sms, tiles);
+    if (splits < 1) splits = 1;
+  }
+  MT_CHECK_CUDA(cudaMemsetAsync(y_f32, 0, size_t(M) * N * sizeof(float), s));
+  return launch_gemm<2>(x, w, nullptr, nullptr, N, nullptr, M, N, K, 0, nullptr, nullptr, 0, 0.f, nullptr, s, y_f32, splits);
 }

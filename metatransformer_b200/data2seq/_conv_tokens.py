@@ -61,8 +61,8 @@ class _ConvTokensFn(torch.autograd.Function):
         d = ctx.wshape[0]
         g2 = g.reshape(-1, d)
         g2 = g2.contiguous() if g2.dtype == torch.bfloat16 else ops.cast(g2.contiguous(), torch.bfloat16)
-        dw = ops.linear_wgrad(g2, ctx.rows)                       # [d, K] bf16 (fp32 accumulation over the tokens)
-        dw = ops.cast(dw, ctx.wdtype) if ctx.wdtype != torch.bfloat16 else dw
+        dw = ops.linear_wgrad(g2, ctx.rows)                       # [d, K] fp32 (split-K tcgen05 GEMM over the tokens)
+        dw = dw if dw.dtype == ctx.wdtype else ops.cast(dw, ctx.wdtype)
         db = None
         if ctx.has_bias:
             db = ops.colsum(g2)

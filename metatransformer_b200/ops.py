@@ -244,8 +244,10 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
 
 
 def ln_fold_bwd(dw_folded: torch.Tensor, weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dyb: torch.Tensor):
-    """(dW fp32 [N,K], dgamma fp32 [K], dbeta fp32 [K]) of a LayerNorm-folded Linear from dWf = dY^T xhat and dyb = colsum(dY)."""
+    """(dW fp32 [N,K], dgamma fp32 [K], dbeta fp32 [K]) of a LayerNorm-folded Linear from dWf = dY^T xhat (fp32) and dyb = colsum(dY)."""
     _require_cuda(dw_folded, weight, gamma, beta, dyb)
+    if dw_folded.dtype != torch.float32:
+        raise ValueError("ln_fold_bwd: dw_folded must be fp32")
     if weight.dtype not in (torch.float32, torch.bfloat16):
         weight = weight.float()
     N, K = weight.shape
@@ -259,10 +261,16 @@ def ln_fold_bwd(dw_folded: torch.Tensor, weight: torch.Tensor, gamma: torch.Tens
     return dw, dg, db
 
 
-def linear_wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW [N,K] = dy[M,N]^T @ x[M,K] (bf16 in, fp32 accumulate over M, bf16 out) via transposed copies + the TN GEMM."""
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, splits: int = 0) -> torch.Tensor:
+    """dW [N,K] fp32 = dy[M,N]^T @ x[M,K]: transposed bf16 copies + the split-K tcgen05 GEMM (fp32 accumulation over M)."""
     dyt, xt = transpose(dy), transpose(x)          # [N, Mp], [K, Mp]
-    return linear(dyt, xt)
+    N, Mp = dyt.shape
+    K = xt.shape[0]
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        check(_lib.load().mt_gemm_bf16_splitk(dyt.data_ptr(), xt.data_ptr(), dw.data_ptr(), N, K, Mp, splits, _stream()),
+              "mt_gemm_bf16_splitk")
+    return dw
 
 
 def im2row1d_circular(x: torch.Tensor) -> torch.Tensor:

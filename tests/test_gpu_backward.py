@@ -143,3 +143,15 @@ def test_trainable_tokenizer_under_frozen_encoder(mt):
     _assert_close(gw.reshape(768, -1), w.grad.reshape(768, -1), rel=3e-2, mx=3e-2, what="conv weight grad")
     _assert_close(gb, b.grad, rel=3e-2, mx=3e-2, what="conv bias grad")
     assert all(p.grad is None for p in enc.parameters())
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(1000, 96, 200, 0), (50176, 768, 768, 0), (4096, 3072, 768, 7), (333, 64, 64, 1)])
+def test_splitk_weight_gradient_gemm(mt, M, N, K, splits):
+    """dW = dY^T X in fp32 through transposed copies + the split-K GEMM (fp32 atomics)"""
+    g = torch.Generator().manual_seed(M + N)
+    dy = _bf16_round(torch.randn(M, N, generator=g) * 0.1)
+    x = _bf16_round(torch.randn(M, K, generator=g))
+    ref = dy.double().t() @ x.double()
+    dw = mt.ops.linear_wgrad(dy.cuda().bfloat16(), x.cuda().bfloat16(), splits)
+    assert dw.dtype == torch.float32 and dw.shape == (N, K)
+    _assert_close(dw, ref, rel=1e-4, mx=1e-4, what=f"split-K wgrad {M}x{N}x{K}")
