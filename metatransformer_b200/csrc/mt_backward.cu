@@ -96,22 +96,52 @@ __global__ void __launch_bounds__(256) gelu_kernel(const __nv_bfloat16* __restri
 }
 
 // dst[c, r] = src[r, c]; dst has leading dimension ldd >= R (columns R..ldd-1 are zero-filled) so that the result can
-// feed the TN GEMM (row pitch must be a multiple of 16 bytes).  32x32 tiles through padded shared memory.
+// feed the TN GEMM (row pitch must be a multiple of 16 bytes).  64x64 tiles: 16-byte global loads and stores on both
+// sides, the transposition itself happens through shared memory (row pitch 66 elements = 33 words -> conflict-free
+// column reads).  Requires C % 8 == 0 and ldd % 8 == 0 for the vector path; a scalar path covers the rest.
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src,
-                                                              __nv_bfloat16* __restrict__ dst, int R, int C, int ldd) {
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+                                                              __nv_bfloat16* __restrict__ dst, int R, int C, int ldd,
+                                                              int vec) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  if (vec) {
+    // load: 64 rows x 8 vectors of 8 elements; thread -> (row = t / 8 + 32 * k, vector = t % 8)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int r = r0 + ty + 8 * k, c = c0 + tx;
-    tile[ty + 8 * k][tx] = (r < R && c < C) ? src[size_t(r) * C + c] : __float2bfloat16_rn(0.f);
-  }
-  __syncthreads();
+    for (int k = 0; k < 2; ++k) {
+      const int rr = (t >> 3) + 32 * k, cv = (t & 7) * 8;
+      const int r = r0 + rr, c = c0 + cv;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < R && c < C) v = *reinterpret_cast<const uint4*>(src + size_t(r) * C + c);
+      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + ty + 8 * k, r = r0 + tx;
-    if (c < C && r < ldd) dst[size_t(c) * ldd + r] = tile[tx][ty + 8 * k];
+      for (int j = 0; j < 8; ++j) tile[rr][cv + j] = e[j];
+    }
+    __syncthreads();
+    // store: output row = source column; thread -> (out row = t / 8 + 32 * k, vector of 8 source rows = t % 8)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int cc = (t >> 3) + 32 * k, rv = (t & 7) * 8;
+      const int c = c0 + cc, r = r0 + rv;
+      if (c < C && r < ldd) {
+        __nv_bfloat16 e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = tile[rv + j][cc];   // rows >= R were loaded as zeros
+        *reinterpret_cast<uint4*>(dst + size_t(c) * ldd + r) = *reinterpret_cast<const uint4*>(e);
+      }
+    }
+  } else {
+    for (int i = t; i < 64 * 64; i += 256) {
+      const int rr = i >> 6, cc = i & 63;
+      const int r = r0 + rr, c = c0 + cc;
+      tile[rr][cc] = (r < R && c < C) ? src[size_t(r) * C + c] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int i = t; i < 64 * 64; i += 256) {
+      const int cc = i >> 6, rr = i & 63;
+      const int c = c0 + cc, r = r0 + rr;
+      if (c < C && r < ldd) dst[size_t(c) * ldd + r] = tile[rr][cc];
+    }
   }
 }
 
@@ -187,9 +217,10 @@ extern "C" int mt_transpose_bf16(const void* src, void* dst, int R, int C, int l
   using namespace mt;
   MT_REQUIRE(src && dst, MT_ERR_BAD_SHAPE, "mt_transpose_bf16: null pointer");
   MT_REQUIRE(R > 0 && C > 0 && ldd >= R, MT_ERR_BAD_SHAPE, "mt_transpose_bf16: need R, C > 0 and ldd >= R");
-  dim3 grid(unsigned(ceil_div(C, 32)), unsigned(ceil_div(ldd, 32)));
+  dim3 grid(unsigned(ceil_div(C, 64)), unsigned(ceil_div(ldd, 64)));
+  const int vec = (C % 8 == 0 && ldd % 8 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) ? 1 : 0;
   transpose_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), R, C, ldd);
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), R, C, ldd, vec);
   MT_CHECK_CUDA(cudaGetLastError());
   return MT_OK;
 }
