@@ -307,7 +307,10 @@ def run_ours(args):
                 "bound": "tensor", "achieved": ach, "peak": sustained_tf, "unit": "TFLOP/s", "frac": ach / sustained_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "flops_per_launch": gemm_flops / n_gemm, "avg_launch_ms": ms["gemm"] / n_gemm,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per gemm_bf16_kernel launch, mean over the four GEMMs of a
+                # layer at this size (qkv 256.0, proj 204.1, fc1 336.5, fc2 457.3 MB; profiles/r1_ncu_layer.md);
+                # algorithmic mean = 350 MB (outputs still sitting in the 126 MB L2 at kernel end are not counted)
+                "traffic": 313.5e6, "traffic_unit": "bytes/launch (ncu --set full, profiles/r1_ncu_layer.md)",
                 "step_breakdown_ms": {k: round(v, 4) for k, v in ms.items()}}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----

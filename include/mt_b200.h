@@ -74,6 +74,9 @@ typedef struct {
   float ln_eps;                 /* used when ln_stats_are_sums */
   float* out_row_sums;          /* [M][2*ceil(N/256)][2] partial statistics of the OUTPUT rows, or NULL */
   int cta_group;                /* 0 auto, 1, 2 */
+  int residual_period;          /* > 0: `residual` is a [residual_period, N] table and output row m adds row
+                                   m % residual_period (positional embedding broadcast over the batch:
+                                   Audio/src/models/ast_models.py:159, Video/models/modeling_finetune.py:434-436) */
 } mt_gemm_opts;
 int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int N, int K, const mt_gemm_opts* opts, void* stream);
 

@@ -33,7 +33,7 @@ class GemmOpts(Structure):
     _fields_ = [
         ("bias", c_void_p), ("residual", c_void_p), ("act", c_int),
         ("ln_colsum", c_void_p), ("ln_row_stats", c_void_p), ("ln_stats_are_sums", c_int), ("ln_eps", c_float),
-        ("out_row_sums", c_void_p), ("cta_group", c_int),
+        ("out_row_sums", c_void_p), ("cta_group", c_int), ("residual_period", c_int),
     ]
 
 

@@ -21,7 +21,9 @@ MT_DEVINL float warp_sum_bw(float v) {
   return v;
 }
 
-// generic d (d % 8 == 0): the row is re-read for the second pass (L1/L2 hits; rows are <= 16 KB)
+// NV > 0: d == NV * 256 exactly and the row's dy / x chunks stay in registers between the two passes (one HBM read);
+// NV == 0: generic d (d % 8 == 0), the row is re-read for the second pass (L1/L2 hits; rows are <= 16 KB).
+template <int NV>
 __global__ void __launch_bounds__(kBwWarps * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                      const float2* __restrict__ stats, const float* __restrict__ gamma,
@@ -32,41 +34,69 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   const size_t base = size_t(row) * d;
   const float2 st = stats[row];
   const float mean = st.x, rstd = st.y;
-  const int nchunks = d >> 3;
+  const float inv_d = 1.0f / float(d);
+  constexpr int NI = NV > 0 ? NV : 1;
+  float gr[NI][8], xh[NI][8];
   float s1 = 0.f, s2 = 0.f;
-  for (int c = lane; c < nchunks; c += 32) {
-    float g[8], xv[8];
-    ld8_bf16(dy + base + c * 8, g);
-    ld8_bf16(x + base + c * 8, xv);
-    if (gamma != nullptr) {
+  const int nchunks = d >> 3;
+  if constexpr (NV > 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= gamma[c * 8 + j];
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      ld8_bf16(dy + base + c * 8, gr[i]);
+      ld8_bf16(x + base + c * 8, xh[i]);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s1 += g[j];
-      s2 = fmaf(g[j], (xv[j] - mean) * rstd, s2);
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (gamma != nullptr) gr[i][j] *= gamma[c * 8 + j];
+        xh[i][j] = (xh[i][j] - mean) * rstd;
+        s1 += gr[i][j];
+        s2 = fmaf(gr[i][j], xh[i][j], s2);
+      }
+    }
+  } else {
+    for (int c = lane; c < nchunks; c += 32) {
+      float g[8], xv[8];
+      ld8_bf16(dy + base + c * 8, g);
+      ld8_bf16(x + base + c * 8, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (gamma != nullptr) g[j] *= gamma[c * 8 + j];
+        s1 += g[j];
+        s2 = fmaf(g[j], (xv[j] - mean) * rstd, s2);
+      }
     }
   }
-  const float inv_d = 1.0f / float(d);
   const float m1 = warp_sum_bw(s1) * inv_d, m2 = warp_sum_bw(s2) * inv_d;
-  for (int c = lane; c < nchunks; c += 32) {
-    float g[8], xv[8], a[8];
-    ld8_bf16(dy + base + c * 8, g);
-    ld8_bf16(x + base + c * 8, xv);
+  auto emit = [&](int c, const float (&g)[8], const float (&xhat)[8]) {
+    float a[8];
     if (add != nullptr) ld8_bf16(add + base + c * 8, a);
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float gj = g[j];
-      if (gamma != nullptr) gj *= gamma[c * 8 + j];
-      const float xh = (xv[j] - mean) * rstd;
-      o[j] = rstd * (gj - m1 - xh * m2) + (add != nullptr ? a[j] : 0.f);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] - m1 - xhat[j] * m2) + (add != nullptr ? a[j] : 0.f);
     uint4 w;
     w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
     w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
     *reinterpret_cast<uint4*>(dx + base + c * 8) = w;
+  };
+  if constexpr (NV > 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) emit(lane + 32 * i, gr[i], xh[i]);
+  } else {
+    for (int c = lane; c < nchunks; c += 32) {
+      float g[8], xv[8];
+      ld8_bf16(dy + base + c * 8, g);
+      ld8_bf16(x + base + c * 8, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (gamma != nullptr) g[j] *= gamma[c * 8 + j];
+        xv[j] = (xv[j] - mean) * rstd;
+      }
+      emit(c, g, xv);
+    }
   }
 }
 
@@ -246,10 +276,16 @@ extern "C" int mt_layernorm_bwd(const void* dy, const void* x, const float* stat
   MT_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
                reinterpret_cast<uintptr_t>(add)) & 15) == 0, MT_ERR_BAD_ALIGN,
              "mt_layernorm_bwd: tensors must be 16-byte aligned");
-  layernorm_bwd_kernel<<<unsigned(ceil_div(M, kBwWarps)), kBwWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x),
-      reinterpret_cast<const float2*>(stats), gamma, reinterpret_cast<const __nv_bfloat16*>(add),
-      reinterpret_cast<__nv_bfloat16*>(dx), M, d);
+  const unsigned grid = unsigned(ceil_div(M, kBwWarps));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  const float2* sp = reinterpret_cast<const float2*>(stats);
+  const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(add);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(dx);
+  if (d == 768) layernorm_bwd_kernel<3><<<grid, kBwWarps * 32, 0, s>>>(dyp, xp, sp, gamma, ap, op, M, d);
+  else if (d == 1024) layernorm_bwd_kernel<4><<<grid, kBwWarps * 32, 0, s>>>(dyp, xp, sp, gamma, ap, op, M, d);
+  else layernorm_bwd_kernel<0><<<grid, kBwWarps * 32, 0, s>>>(dyp, xp, sp, gamma, ap, op, M, d);
   MT_CHECK_CUDA(cudaGetLastError());
   return MT_OK;
 }

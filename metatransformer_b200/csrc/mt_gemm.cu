@@ -51,8 +51,10 @@ struct GemmCfg {
 
 struct GemmParams {
   const float* bias;            // [N] fp32 or nullptr
-  const __nv_bfloat16* resid;   // [M, ldr] bf16 or nullptr
+  const __nv_bfloat16* resid;   // [M, ldr] bf16 (or [resid_period, ldr], see below) or nullptr
   int ldr;
+  int resid_period;             // > 0: output row m reads residual row m % resid_period (a [n, d] positional table
+                                // broadcast over the batch: tokenizer GEMMs)
   int M, N, K;
   int act;                      // 0 = identity, 1 = exact-erf GELU, 2 = multiply by gelu'(resid) (backward)
   int num_m_tiles, num_n_tiles;
@@ -290,7 +292,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // residual slices are fetched one 32-column slice ahead of their use (the first one before the accumulator
       // is even ready), so the L2/HBM latency hides behind the MMAs of this tile and the math of the previous slice
       const bool row_ok = (p.resid != nullptr) && (row < p.M);
-      const __nv_bfloat16* rrow = row_ok ? p.resid + size_t(row) * p.ldr : nullptr;
+      const __nv_bfloat16* rrow =
+          row_ok ? p.resid + size_t(p.resid_period > 0 ? row % p.resid_period : row) * p.ldr : nullptr;
       uint4 rv_next[4];
       auto load_resid = [&](int sc_, uint4 (&dst)[4]) {
         const int c_ = col0 + 32 * sc_;
@@ -427,7 +430,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 template <int CG>
 static int launch_gemm(const void* x, const void* w, const float* bias, const void* resid, int ldr, void* y, int M,
                        int N, int K, int act, const float* row_stats, const float* colsum, int ln_sums, float ln_eps,
-                       float* out_row_sums, cudaStream_t stream, float* out_f32 = nullptr, int split_k = 1) {
+                       float* out_row_sums, cudaStream_t stream, float* out_f32 = nullptr, int split_k = 1,
+                       int resid_period = 0) {
   using Cfg = GemmCfg<CG>;
   CUtensorMap tm_a, tm_b, tm_y;
   {
@@ -457,6 +461,7 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   p.bias = bias;
   p.resid = reinterpret_cast<const __nv_bfloat16*>(resid);
   p.ldr = ldr;
+  p.resid_period = resid_period;
   p.M = M; p.N = N; p.K = K;
   p.act = act;
   p.row_stats = reinterpret_cast<const float2*>(row_stats);
@@ -502,7 +507,8 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
 
 static int gemm_entry(const char* who, const void* x, const void* w, const float* bias, const void* residual, void* y,
                       int M, int N, int K, int act, const float* row_stats, const float* colsum, int cta_group,
-                      void* stream, int ln_sums = 0, float ln_eps = 0.f, float* out_row_sums = nullptr) {
+                      void* stream, int ln_sums = 0, float ln_eps = 0.f, float* out_row_sums = nullptr,
+                      int resid_period = 0) {
   using namespace mt;
   MT_REQUIRE(x && w && y, MT_ERR_BAD_SHAPE, "%s: null pointer", who);
   MT_REQUIRE(M > 0 && N > 0 && K > 0, MT_ERR_BAD_SHAPE, "%s: M,N,K must be positive (got %d,%d,%d)", who, M, N, K);
@@ -517,6 +523,8 @@ static int gemm_entry(const char* who, const void* x, const void* w, const float
   MT_REQUIRE(act == 0 || act == 1 || act == 2, MT_ERR_UNSUPPORTED,
              "%s: act must be 0 (none), 1 (gelu) or 2 (times gelu'(residual))", who);
   MT_REQUIRE(act != 2 || residual != nullptr, MT_ERR_BAD_SHAPE, "%s: act 2 needs the pre-activation as `residual`", who);
+  MT_REQUIRE(resid_period >= 0 && (resid_period == 0 || (residual != nullptr && act != 2)), MT_ERR_BAD_SHAPE,
+             "%s: residual_period needs a residual table and act != 2", who);
   MT_REQUIRE((row_stats == nullptr) == (colsum == nullptr), MT_ERR_BAD_SHAPE,
              "%s: row_stats and colsum must be given together", who);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -531,9 +539,11 @@ static int gemm_entry(const char* who, const void* x, const void* w, const float
   }
   MT_REQUIRE((reinterpret_cast<uintptr_t>(out_row_sums) & 7) == 0, MT_ERR_BAD_ALIGN, "%s: out_row_sums must be 8-byte aligned", who);
   if (cta_group == 1)
-    return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s);
+    return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s,
+                          nullptr, 1, resid_period);
   if (cta_group == 2)
-    return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s);
+    return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s,
+                          nullptr, 1, resid_period);
   set_error("%s: cta_group must be 0 (auto), 1 or 2", who);
   return MT_ERR_UNSUPPORTED;
 }
@@ -561,7 +571,7 @@ extern "C" int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int
     return MT_ERR_BAD_SHAPE;
   }
   return gemm_entry("mt_gemm_bf16_ex", x, w, o->bias, o->residual, y, M, N, K, o->act, o->ln_row_stats, o->ln_colsum,
-                    o->cta_group, stream, o->ln_stats_are_sums, o->ln_eps, o->out_row_sums);
+                    o->cta_group, stream, o->ln_stats_are_sums, o->ln_eps, o->out_row_sums, o->residual_period);
 }
 
 // y_f32[M,N] += x[M,K] @ w[N,K]^T with the K range split over `splits` CTAs per output tile (fp32 atomics).

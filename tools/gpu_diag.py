@@ -181,6 +181,21 @@ def group_perf():
         ms = timeit(lambda: ops.attention(qkv, H, out=out))
         fl = 4.0 * B * H * N * N * 64
         print(f"[perf] attention B={B} N={N} H={H}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for (B, N, H) in [(256, 196, 12), (32, 1568, 16)]:
+        qkv = torch.randn(B, N, 3 * H * 64, device=dev).bfloat16()
+        o, lse = ops.attention_lse(qkv, H)
+        do = torch.randn_like(o)
+        ms = timeit(lambda: ops.attention_bwd(qkv, o, do, lse, H), iters=10)
+        fl = 10.0 * B * H * N * N * 64
+        print(f"[perf] attention_bwd B={B} N={N} H={H}: {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    xx = torch.randn(M, 768, device=dev).bfloat16()
+    st = ops.row_stats(xx)
+    dyy = torch.randn_like(xx)
+    ms = timeit(lambda: ops.layernorm_bwd(dyy, xx, st, None, dyy))
+    print(f"[perf] layernorm_bwd M={M} d=768: {ms:.4f} ms  {M * 768 * 8 / ms / 1e6:.1f} GB/s", flush=True)
+    tt = torch.randn(M, 3072, device=dev).bfloat16()
+    ms = timeit(lambda: ops.transpose(tt), iters=10)
+    print(f"[perf] transpose M={M} x 3072: {ms:.4f} ms  {M * 3072 * 4 / ms / 1e6:.1f} GB/s", flush=True)
     x = torch.randn(M, 768, device=dev).bfloat16()
     g = torch.ones(768, device=dev)
     bb = torch.zeros(768, device=dev)
