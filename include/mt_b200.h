@@ -140,6 +140,37 @@ int mt_im2row1d_circular(const void* x, int x_dtype, void* rows, int B, int T, i
  * Hyper-spectrum/metatransformer.py:155-157); bf16, d % 8 == 0 ---- */
 int mt_prepend_row(const void* tok, const void* first, void* out, int B, int n, int d, void* stream);
 
+/* ---- steps either side of the encoder ---------------------------------------------------
+ * mt_assemble_tokens: out[b, i, :] = (i < k ? prefix[i] : tok[b, i-k]) + pos[i]   (bf16; prefix [k,d] may be NULL when
+ *   k == 0, pos [(n+k), d] may be NULL): cls / dist tokens and the positional embedding in one HBM pass
+ *   (Audio/src/models/ast_models.py:157-159, Hyper-spectrum/metatransformer.py:155-158).
+ * mt_pool_layernorm: the final LayerNorm fused with the pooling each fork applies before its head; x [B,N,d] bf16,
+ *   out [B,d] bf16.  MT_POOL_FIRST: norm(x)[:,0] (Video/models/modeling_finetune.py:449, Hyper-spectrum/
+ *   metatransformer.py:163-165); MT_POOL_MEAN: fc_norm(x.mean(1)) (modeling_finetune.py:446-447);
+ *   MT_POOL_FIRST_TWO: (norm(x)[:,0] + norm(x)[:,1]) / 2 (ast_models.py:163-164).
+ * mt_pool_layernorm_bwd: its autograd: dx [B,N,d] bf16 (zero for tokens that are not pooled), dgamma / dbeta fp32 [d]
+ *   (either may be NULL; zeroed inside, accumulated with fp32 atomics over the batch).                              */
+typedef enum { MT_POOL_FIRST = 0, MT_POOL_MEAN = 1, MT_POOL_FIRST_TWO = 2 } mt_pool_mode;
+int mt_assemble_tokens(const void* tok, const void* prefix, const void* pos, void* out, int B, int n, int k, int d,
+                       void* stream);
+int mt_pool_layernorm(const void* x, const float* gamma, const float* beta, void* out, int B, int N, int d, int mode,
+                      float eps, void* stream);
+int mt_pool_layernorm_bwd(const void* dy, const void* x, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                          int B, int N, int d, int mode, float eps, void* stream);
+
+/* ---- training-time dropout / stochastic depth ---------------------------------------------
+ * out[r, c] = residual[r, c] + row_scale[r / rows_per_scale] * keep(r, c) / (1 - p) * x[r, c]      (bf16 [rows, d])
+ * keep() is a Philox4x32-10 stream addressed by (seed, offset + element index / 8): the same (seed, offset) gives the
+ * same mask, so the backward pass calls this again on the gradient instead of storing the mask.  residual and
+ * row_scale may be NULL.  nn.Dropout in Mlp / Attention.proj_drop (PointCloud/openpoints/models/layers/mlp.py:31-34,
+ * attention.py:37) = p > 0, no row_scale; timm DropPath (attention.py:48,56-57) = p = 0 with row_scale[b] =
+ * bernoulli(keep)/keep per sample and rows_per_scale = tokens per sample.  A call advances the stream by rows*d/8. */
+int mt_dropout(const void* x, const void* residual, const float* row_scale, int rows_per_scale, void* out,
+               long long rows, int d, float p, unsigned long long seed, unsigned long long offset, void* stream);
+
+/* ---- text features: zero padding to the encoder width (Data2Seq/Text.py:15-19); dtype fp32 or bf16 ---- */
+int mt_pad_cols(const void* x, void* out, int dtype, long long rows, int c_in, int c_out, void* stream);
+
 /* ---- dtype conversion helper (weights packing, fp32 activations at the boundary) ---- */
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p, POINTER, Structure
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p, POINTER, Structure
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -19,7 +19,8 @@ EXPORTED_SYMBOLS = (
     "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_gemm_bf16_ln", "mt_gemm_bf16_ex", "mt_gemm_bf16_splitk", "mt_row_stats",
     "mt_fold_layernorm", "mt_layernorm", "mt_layernorm_bwd", "mt_gelu", "mt_transpose_bf16", "mt_colsum", "mt_ln_fold_bwd", "mt_attention_fwd",
     "mt_attention_fwd_lse", "mt_attention_bwd_workspace_bytes", "mt_attention_bwd",
-    "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
+    "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_assemble_tokens", "mt_pool_layernorm", "mt_pool_layernorm_bwd",
+    "mt_dropout", "mt_pad_cols", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
     "mt_encoder_forward", "mt_encoder_launches_per_forward",
 )
 
@@ -100,6 +101,17 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_im2row1d_circular.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.mt_prepend_row.restype = c_int
     lib.mt_prepend_row.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.mt_assemble_tokens.restype = c_int
+    lib.mt_assemble_tokens.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_void_p]
+    lib.mt_pool_layernorm.restype = c_int
+    lib.mt_pool_layernorm.argtypes = [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]
+    lib.mt_pool_layernorm_bwd.restype = c_int
+    lib.mt_pool_layernorm_bwd.argtypes = [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p]
+    lib.mt_dropout.restype = c_int
+    lib.mt_dropout.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_longlong, c_int, c_float, c_ulonglong,
+                               c_ulonglong, c_void_p]
+    lib.mt_pad_cols.restype = c_int
+    lib.mt_pad_cols.argtypes = [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_void_p]
     lib.mt_cast.restype = c_int
     lib.mt_cast.argtypes = [c_void_p, c_int, c_void_p, c_int, c_size_t, c_void_p]
     lib.mt_encoder_create.restype = c_int

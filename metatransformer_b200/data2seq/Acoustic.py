@@ -25,8 +25,8 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=(fstride, tstride))
         self.token_dtype = token_dtype
 
-    def forward(self, x):
+    def forward(self, x, pos_embed=None, prefix_tokens=None):
         # x: (B, in_chans, F, T)  (Audio/src/models/ast_models.py:152-155 builds it from (B, T, F))
         k = (1,) + tuple(self.patch_size)
         s = (1, self.fstride, self.tstride)
-        return conv_tokens(self, self.proj, x.unsqueeze(2), k, s, self.token_dtype)
+        return conv_tokens(self, self.proj, x.unsqueeze(2), k, s, self.token_dtype, pos_embed, prefix_tokens)

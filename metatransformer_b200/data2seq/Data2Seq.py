@@ -12,14 +12,18 @@ are kept and the *intended* semantics implemented:
                              `cin=` typo fixed)
   hyper                    : Hyper_Spectrum.PatchEmbed(embed_dim=dim): Linear + cls + pos (Data2Seq.py:33-34; working
                              form Hyper-spectrum/metatransformer.py:152-159)
-  text, graph              : not built yet -> NotImplementedError
+  text                     : the reference constructs a CLIPTokenizer that returns ids, not embeddings, and its padding
+                             branch is dead code (Data2Seq.py:27-28,50-52); here pre-computed (B, c) sentence features
+                             are zero-padded to `dim` as Text.zero_padding does (Text.py:15-19) -> (B, 1, dim)
+  graph                    : not built (ragged host-side batching + QR-based node identifiers, Graph.py:234-305; its
+                             encoder also needs key-padding masks the timm Block does not have) -> NotImplementedError
 """
 import torch.nn as nn
 
-from . import Acoustic, Hyper_Spectrum, Image, Time_Series, Video
+from . import Acoustic, Hyper_Spectrum, Image, Text, Time_Series, Video
 
 _IMAGE_LIKE = ('image', 'infrared', 'x-ray')
-_NEXT = ('text', 'graph')
+_NEXT = ('graph',)
 
 
 class Data2Seq(nn.Module):
@@ -38,6 +42,8 @@ class Data2Seq(nn.Module):
             self.embed = Hyper_Spectrum.PatchEmbed(embed_dim=self.embed_dim, token_dtype=token_dtype)
         elif self.modality in ('time-series', 'imu'):
             self.embed = Time_Series.DataEmbedding(c_in=1, d_model=self.embed_dim, token_dtype=token_dtype)
+        elif self.modality == 'text':
+            self.embed = Text.TextFeaturePad(embed_dim=self.embed_dim)
         elif self.modality in _NEXT:
             raise NotImplementedError(f"Data2Seq modality '{modality}' is not built on the B200 path yet "
                                       "(SURVEY.md §8f rank 3)")

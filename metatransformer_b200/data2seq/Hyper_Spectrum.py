@@ -39,17 +39,9 @@ class PatchEmbed(nn.Module):
         x2 = x2 if x2.dtype == torch.bfloat16 else ops.cast(x2 if x2.dtype == torch.float32 else x2.float(), torch.bfloat16)
         w = _packed(self, "w", self.patch_to_embedding.weight, torch.bfloat16)
         bias = _packed(self, "b", self.patch_to_embedding.bias, torch.float32)
-        # one-time small tables: pos rows 1..n tiled over the batch (residual operand) and cls + pos[0]
-        cache = self.__dict__.setdefault("_mt_pack_cache", {})
-        key = (self.pos_embedding.data_ptr(), self.pos_embedding._version, self.cls_token._version, b, n, str(x.device))
-        hit = cache.get("pos")
-        if hit is None or hit[0] != key:
-            pos = self.pos_embedding.detach()[0, :n + 1].float()
-            body = ops.cast(pos[1:].unsqueeze(0).expand(b, n, -1).reshape(b * n, -1).contiguous(), torch.bfloat16)
-            first = ops.cast((self.cls_token.detach()[0, 0].float() + pos[0]).contiguous(), torch.bfloat16)
-            hit = (key, body, first)
-            cache["pos"] = hit
-        tok = ops.linear(x2, w, bias, residual=hit[1])                 # [b*n, d] = patches W^T + b + pos[1:]
-        out = ops.prepend_row(tok.view(b, n, -1), hit[2])              # [b, n+1, d]
+        pos = _packed(self, "pos", self.pos_embedding, torch.bfloat16)[0, :n + 1].contiguous()      # [n+1, d]
+        cls = _packed(self, "cls", self.cls_token, torch.bfloat16).view(1, -1)
+        tok = ops.linear(x2, w, bias)                                  # [b*n, d] = patches W^T + b
+        out = ops.assemble_tokens(tok.view(b, n, -1), cls, pos)        # [b, n+1, d] = [cls ; tok] + pos[:n+1]
         out_dtype = self.token_dtype or (x.dtype if x.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32)
         return out if out_dtype == torch.bfloat16 else ops.cast(out, out_dtype)

@@ -20,9 +20,9 @@ class PatchEmbed(nn.Module):
         self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
         self.token_dtype = token_dtype
 
-    def forward(self, x):
+    def forward(self, x, pos_embed=None, prefix_tokens=None):
         B, C, H, W = x.shape
         assert H == self.img_size[0] and W == self.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
         k = (1,) + tuple(self.patch_size)
-        return conv_tokens(self, self.proj, x.unsqueeze(2), k, k, self.token_dtype)
+        return conv_tokens(self, self.proj, x.unsqueeze(2), k, k, self.token_dtype, pos_embed, prefix_tokens)

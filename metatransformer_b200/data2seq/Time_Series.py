@@ -47,12 +47,11 @@ class DataEmbedding(nn.Module):
         self.token_dtype = token_dtype
         self._pe_cache = {}
 
-    def _pe_rows(self, B, T, device):
-        key = (B, T, str(device))
+    def _pe_rows(self, T, device):
+        key = (T, str(device))
         pe = self._pe_cache.get(key)
         if pe is None:
-            pe = ops.cast(self.position_embedding.pe[0, :T].to(device).contiguous(), torch.bfloat16)
-            pe = pe.unsqueeze(0).expand(B, T, pe.shape[-1]).reshape(B * T, -1).contiguous()   # one-time table expansion
+            pe = ops.cast(self.position_embedding.pe[0, :T].to(device).contiguous(), torch.bfloat16)   # [T, d] table
             if len(self._pe_cache) > 8:
                 self._pe_cache.clear()
             self._pe_cache[key] = pe
@@ -82,7 +81,7 @@ class DataEmbedding(nn.Module):
             w2[:, :3 * C] = w.detach().reshape(d, 3 * C).float()
             hit = (key, ops.cast(w2, torch.bfloat16))
             cache["w2d"] = hit
-        tok = ops.linear(rows, hit[1], None, residual=self._pe_rows(B, T, x.device))
+        tok = ops.linear(rows, hit[1], None, residual=self._pe_rows(T, x.device), residual_period=T)   # + PE[t]
         out_dtype = self.token_dtype or xin.dtype
         if out_dtype != torch.bfloat16:
             tok = ops.cast(tok, out_dtype)

@@ -125,8 +125,10 @@ class FusedEncoder(nn.Module):
             raise RuntimeError("FusedEncoder: CUDA (B200) tensors only; there is no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.blocks.parameters())):
             raise NotImplementedError("FusedEncoder is forward-only; wrap the call in torch.no_grad()")
-        if self.training and any(m.p > 0 for m in self.blocks.modules() if isinstance(m, nn.Dropout)):
-            raise NotImplementedError("FusedEncoder: dropout in training mode is not supported")
+        if self.training and any(m.p > 0 for m in self.blocks.modules() if isinstance(m, nn.Dropout)) or any(
+                getattr(b, "_is_stochastic", lambda: False)() for b in self.blocks):
+            raise NotImplementedError("FusedEncoder: dropout / drop-path in training mode is not supported; call the "
+                                      "Blocks (nn.Sequential) for training")
         self._ensure_handle()
         lib = _lib.load()
         B, N, C = x.shape

@@ -51,8 +51,9 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, gelu: bool = False, cta_group: int = 0,
-           out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = act(x @ weight.T + bias) (+ residual).  x [M,K] bf16, weight [N,K] bf16, bias [N] fp32, residual [M,N] bf16."""
+           out: Optional[torch.Tensor] = None, residual_period: int = 0) -> torch.Tensor:
+    """y = act(x @ weight.T + bias) (+ residual).  x [M,K] bf16, weight [N,K] bf16, bias [N] fp32, residual [M,N] bf16 —
+    or, with residual_period = n > 0, a [n,N] table of which output row m adds row m % n (positional embedding)."""
     _require_cuda(x, weight, bias, residual, out)
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("linear: x and weight must be bf16")
@@ -64,13 +65,19 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     N, K2 = weight.shape
     if K != K2:
         raise ValueError(f"linear: K mismatch {K} vs {K2}")
-    if residual is not None and tuple(residual.shape) != (M, N):
+    if residual is not None and tuple(residual.shape) != ((residual_period or M), N):
         raise ValueError("linear: residual shape mismatch")
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        check(_lib.load().mt_gemm_bf16(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
-                                       M, N, K, 1 if gelu else 0, cta_group, _stream()), "mt_gemm_bf16")
+        if residual_period > 0:
+            o = _lib.GemmOpts(bias=_ptr(bias), residual=_ptr(residual), act=1 if gelu else 0, cta_group=cta_group,
+                              residual_period=residual_period)
+            check(_lib.load().mt_gemm_bf16_ex(x.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, o, _stream()),
+                  "mt_gemm_bf16_ex")
+        else:
+            check(_lib.load().mt_gemm_bf16(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
+                                           M, N, K, 1 if gelu else 0, cta_group, _stream()), "mt_gemm_bf16")
     return out
 
 
@@ -308,3 +315,84 @@ def im2row(x: torch.Tensor, kernel: Sequence[int], stride: Sequence[int]) -> Tup
         check(_lib.load().mt_im2row(x.data_ptr(), _DT[x.dtype], rows.data_ptr(), B, C, T, H, W, kt, kh, kw, st, sh, sw,
                                     _stream()), "mt_im2row")
     return rows, (Tp, Hp, Wp)
+
+
+POOL_FIRST, POOL_MEAN, POOL_FIRST_TWO = 0, 1, 2
+
+
+def assemble_tokens(tok: torch.Tensor, prefix: Optional[torch.Tensor] = None,
+                    pos: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] = [prefix ; tok[b]] + pos: tok [B,n,d], prefix [k,d], pos [n+k,d], all bf16 -> [B,n+k,d]."""
+    _require_cuda(tok, prefix, pos)
+    B, n, d = tok.shape
+    k = 0 if prefix is None else prefix.shape[0]
+    if any(t is not None and t.dtype != torch.bfloat16 for t in (tok, prefix, pos)):
+        raise ValueError("assemble_tokens: bf16 tensors only")
+    if pos is not None and tuple(pos.shape) != (n + k, d):
+        raise ValueError(f"assemble_tokens: pos must be [{n + k}, {d}], got {tuple(pos.shape)}")
+    out = torch.empty((B, n + k, d), dtype=torch.bfloat16, device=tok.device)
+    with torch.cuda.device(tok.device):
+        check(_lib.load().mt_assemble_tokens(tok.data_ptr(), _ptr(prefix), _ptr(pos), out.data_ptr(), B, n, k, d,
+                                             _stream()), "mt_assemble_tokens")
+    return out
+
+
+def pool_layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, mode: int, eps: float = 1e-5) -> torch.Tensor:
+    """Final LayerNorm fused with the pooling: x [B,N,d] bf16 -> [B,d] bf16 (POOL_FIRST / POOL_MEAN / POOL_FIRST_TWO)."""
+    _require_cuda(x, weight, bias)
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.float32 or bias.dtype != torch.float32:
+        raise ValueError("pool_layernorm: x bf16, weight/bias fp32")
+    B, N, d = x.shape
+    out = torch.empty((B, d), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_pool_layernorm(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), B, N, d,
+                                            int(mode), float(eps), _stream()), "mt_pool_layernorm")
+    return out
+
+
+def pool_layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, mode: int, eps: float = 1e-5,
+                       param_grads: bool = True):
+    """Autograd of pool_layernorm: (dx [B,N,d] bf16, dweight [d] fp32 | None, dbias [d] fp32 | None)."""
+    _require_cuda(dy, x, weight)
+    B, N, d = x.shape
+    if dy.dtype != torch.bfloat16 or tuple(dy.shape) != (B, d):
+        raise ValueError("pool_layernorm_bwd: dy must be bf16 [B,d]")
+    dx = torch.empty_like(x)
+    dg = torch.empty(d, dtype=torch.float32, device=x.device) if param_grads else None
+    db = torch.empty(d, dtype=torch.float32, device=x.device) if param_grads else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_pool_layernorm_bwd(dy.data_ptr(), x.data_ptr(), weight.data_ptr(), dx.data_ptr(), _ptr(dg),
+                                                _ptr(db), B, N, d, int(mode), float(eps), _stream()),
+              "mt_pool_layernorm_bwd")
+    return dx, dg, db
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int, residual: Optional[torch.Tensor] = None,
+            row_scale: Optional[torch.Tensor] = None, rows_per_scale: int = 1,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = residual + row_scale[row // rows_per_scale] * keep / (1 - p) * x on x [rows, d] bf16; the mask is a pure
+    function of (seed, offset, element index), so calling it again on a gradient replays the forward mask."""
+    _require_cuda(x, residual, row_scale, out)
+    if x.dtype != torch.bfloat16 or (residual is not None and residual.dtype != torch.bfloat16):
+        raise ValueError("dropout: bf16 tensors only")
+    if row_scale is not None and row_scale.dtype != torch.float32:
+        raise ValueError("dropout: row_scale must be fp32")
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_dropout(x.data_ptr(), _ptr(residual), _ptr(row_scale), int(rows_per_scale), out.data_ptr(),
+                                     rows, d, float(p), int(seed) & (2 ** 64 - 1), int(offset), _stream()), "mt_dropout")
+    return out
+
+
+def pad_cols(x: torch.Tensor, width: int) -> torch.Tensor:
+    """Zero-pad the last dim of x [rows, c] (fp32/bf16) to `width` columns (Data2Seq/Text.py:15-19)."""
+    _require_cuda(x)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("pad_cols: fp32 or bf16 only")
+    rows, c = x.shape
+    out = torch.empty((rows, width), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_pad_cols(x.data_ptr(), out.data_ptr(), _DT[x.dtype], rows, c, width, _stream()), "mt_pad_cols")
+    return out

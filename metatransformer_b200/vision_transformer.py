@@ -35,8 +35,17 @@ class DropPath(nn.Module):
     def forward(self, x):
         if self.drop_prob == 0.0 or not self.training:
             return x
-        raise NotImplementedError("DropPath with rate > 0 in training mode is not implemented on the B200 path yet "
-                                  "(SURVEY.md §8f rank 2)")
+        raise NotImplementedError("DropPath as a stand-alone module is not built; inside Block the stochastic depth is "
+                                  "fused with the residual add (mt_dropout)")
+
+
+def _philox_reserve(device: torch.device, n_elements: int):
+    """(seed, offset) for a mask over n_elements, drawn from torch's CUDA generator of `device` so that
+    torch.cuda.manual_seed / torch.utils.checkpoint's RNG stashing govern these masks exactly like nn.Dropout's."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(offset + (n_elements // 8 + 4) // 4 * 4)
+    return seed, offset
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -98,7 +107,7 @@ class Mlp(nn.Module):
 
     def _check_train(self):
         if self.training and self.drop.p > 0:
-            raise NotImplementedError("Mlp: dropout p > 0 in training mode is not implemented on the B200 path yet")
+            raise NotImplementedError("Mlp: dropout p > 0 in training mode is built at Block granularity only")
 
     def _forward_2d(self, h: torch.Tensor, residual: Optional[torch.Tensor]) -> torch.Tensor:
         w1 = _packed(self, "fc1.weight", self.fc1.weight, torch.bfloat16)
@@ -130,8 +139,11 @@ class Attention(nn.Module):
             raise ValueError("Attention: dim must be divisible by num_heads")
 
     def _check_train(self):
-        if self.training and (self.attn_drop.p > 0 or self.proj_drop.p > 0):
-            raise NotImplementedError("Attention: dropout p > 0 in training mode is not implemented on the B200 path yet")
+        if self.training and self.attn_drop.p > 0:
+            raise NotImplementedError("Attention: attn_drop > 0 in training mode is not implemented on the B200 path "
+                                      "(the mask would have to be generated inside the attention kernels)")
+        if self.training and self.proj_drop.p > 0:
+            raise NotImplementedError("Attention: proj_drop > 0 in training mode is built at Block granularity only")
 
     def _forward_2d(self, h: torch.Tensor, B: int, N: int, residual: Optional[torch.Tensor]) -> torch.Tensor:
         wq = _packed(self, "qkv.weight", self.qkv.weight, torch.bfloat16)
@@ -230,40 +242,90 @@ class Block(nn.Module):
         cache[name] = (key, wt)
         return wt
 
+    def _is_stochastic(self) -> bool:
+        p_path = self.drop_path.drop_prob if isinstance(self.drop_path, DropPath) else 0.0
+        return self.training and (self.attn.proj_drop.p > 0 or self.mlp.drop.p > 0 or p_path > 0)
+
+    @staticmethod
+    def _replay(g: torch.Tensor, p: float, key, rs, N: int) -> torch.Tensor:
+        """Apply a forward dropout / drop-path mask to a gradient (identity when that site had neither)."""
+        if p == 0 and rs is None:
+            return g
+        return ops.dropout(g, p, *key, row_scale=rs, rows_per_scale=N)
+
+    def _drop_config(self, B: int, device: torch.device):
+        """Training-time stochastic pieces of this Block, or None: nn.Dropout after proj / inside and after the Mlp
+        (attention.py:37, mlp.py:31-34) and per-sample DropPath on both residual branches (attention.py:56-57)."""
+        if not self.training:
+            return None
+        p_proj, p_mlp = self.attn.proj_drop.p, self.mlp.drop.p
+        p_path = self.drop_path.drop_prob if isinstance(self.drop_path, DropPath) else 0.0
+        if p_proj == 0 and p_mlp == 0 and p_path == 0:
+            return None
+        cfg = {"p_proj": p_proj, "p_mlp": p_mlp, "rs1": None, "rs2": None}
+        if p_path > 0:
+            keep = 1.0 - p_path
+            rs = torch.empty((2, B), dtype=torch.float32, device=device).bernoulli_(keep).div_(keep)   # timm DropPath
+            cfg["rs1"], cfg["rs2"] = rs[0], rs[1]
+        return cfg
+
     def _forward_train(self, x2: torch.Tensor, B: int, N: int):
         """Forward that keeps what the backward needs (qkv, attention output + lse, the pre-GELU activation)."""
         attn, mlp = self.attn, self.mlp
+        drop = self._drop_config(B, x2.device)
         wq, csq, bq = self._folded("fold.qkv", attn.qkv, self.norm1)
         stats1 = ops.row_stats(x2, self.norm1.eps)
         qkv = ops.linear_ln(x2, wq, bq, csq, stats1)
         o, lse2 = ops.attention_lse(qkv.view(B, N, -1), attn.num_heads, attn.scale)
-        x_mid = ops.linear(o.view(B * N, -1), _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16),
-                           _packed(attn, "proj.bias", attn.proj.bias, torch.float32), residual=x2)
+        wp = _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16)
+        bp = _packed(attn, "proj.bias", attn.proj.bias, torch.float32)
+        if drop is None:
+            x_mid = ops.linear(o.view(B * N, -1), wp, bp, residual=x2)
+        else:
+            branch = ops.linear(o.view(B * N, -1), wp, bp)
+            drop["k1"] = _philox_reserve(x2.device, branch.numel())
+            x_mid = ops.dropout(branch, drop["p_proj"], *drop["k1"], residual=x2, row_scale=drop["rs1"],
+                                rows_per_scale=N, out=branch)
         w1, cs1, b1 = self._folded("fold.fc1", mlp.fc1, self.norm2)
         stats2 = ops.row_stats(x_mid, self.norm2.eps)
         u = ops.linear_ln(x_mid, w1, b1, cs1, stats2, gelu=False)
         hid = ops.gelu(u)
-        out = ops.linear(hid, _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16),
-                         _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32), residual=x_mid)
-        return out, (x2, stats1, qkv, o, lse2, x_mid, stats2, u)
+        w2 = _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16)
+        b2 = _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32)
+        if drop is None:
+            out = ops.linear(hid, w2, b2, residual=x_mid)
+        else:
+            if drop["p_mlp"] > 0:
+                drop["kh"] = _philox_reserve(x2.device, hid.numel())
+                hid = ops.dropout(hid, drop["p_mlp"], *drop["kh"], out=hid)
+            branch = ops.linear(hid, w2, b2)
+            drop["k2"] = _philox_reserve(x2.device, branch.numel())
+            out = ops.dropout(branch, drop["p_mlp"], *drop["k2"], residual=x_mid, row_scale=drop["rs2"],
+                              rows_per_scale=N, out=branch)
+        return out, (x2, stats1, qkv, o, lse2, x_mid, stats2, u, drop)
 
     def _backward_2d(self, g2: torch.Tensor, saved, B: int, N: int) -> torch.Tensor:
         """dX of the Block for frozen weights (dgrad only): 4 GEMMs + attention backward + 2 LayerNorm backwards."""
-        x2, stats1, qkv, o, lse2, x_mid, stats2, u = saved
+        x2, stats1, qkv, o, lse2, x_mid, stats2, u, drop = saved
         attn, mlp = self.attn, self.mlp
         M = B * N
+        # gradient entering the mlp branch (after its dropout / stochastic depth, replayed from the saved Philox keys)
+        gb2 = g2 if drop is None else self._replay(g2, drop["p_mlp"], drop["k2"], drop["rs2"], N)
         w2t = self._transposed("t.fc2", _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16))
-        du = ops.linear_gelu_grad(g2, w2t, u)                                   # dL/du = (g W2) * gelu'(u)
+        du = ops.linear_gelu_grad(gb2, w2t, u)                                  # dL/du = (g W2) * gelu'(u)
+        if drop is not None and drop["p_mlp"] > 0:
+            du = ops.dropout(du, drop["p_mlp"], *drop["kh"], out=du)            # the mask sits between gelu and fc2
         w1f = self._folded("fold.fc1", mlp.fc1, self.norm2)[0]
         dxh2 = ops.linear(du, self._transposed("t.fc1f", w1f))                  # dL/dxhat (gamma already folded in)
         g1 = ops.layernorm_bwd(dxh2, x_mid, stats2, None, add=g2)               # + residual branch
+        gb1 = g1 if drop is None else self._replay(g1, drop["p_proj"], drop["k1"], drop["rs1"], N)
         wpt = self._transposed("t.proj", _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16))
-        do = ops.linear(g1, wpt)
+        do = ops.linear(gb1, wpt)
         dqkv = ops.attention_bwd(qkv.view(B, N, -1), o, do.view(B, N, -1), lse2, attn.num_heads, attn.scale)
         wqf = self._folded("fold.qkv", attn.qkv, self.norm1)[0]
         dxh1 = ops.linear(dqkv.view(M, -1), self._transposed("t.qkvf", wqf))
         dx = ops.layernorm_bwd(dxh1, x2, stats1, None, add=g1)
-        return dx, (g2, du, g1, dqkv.view(M, -1))
+        return dx, (gb2, du, gb1, dqkv.view(M, -1))
 
     _PARAM_ORDER = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
                     "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",
@@ -277,8 +339,8 @@ class Block(nn.Module):
         """Fine-tune mode: gradients of all 12 parameters, in `_PARAM_ORDER`.
         Every Linear's dW = dY^T X runs as the TN GEMM on transposed copies (fp32 accumulation over the tokens, bf16
         result); the two LayerNorm-folded Linears are un-folded by mt_ln_fold_bwd."""
-        x2, stats1, qkv, o, lse2, x_mid, stats2, u = saved
-        g2, du, g1, dqkv = grads
+        x2, stats1, qkv, o, lse2, x_mid, stats2, u, drop = saved
+        g2, du, g1, dqkv = grads          # g2 / g1: gradients entering the fc2 / proj branches (dropout already replayed)
         attn, mlp = self.attn, self.mlp
         d = x2.shape[1]
         cache = self.__dict__.setdefault("_mt_pack_cache", {})
@@ -288,6 +350,8 @@ class Block(nn.Module):
         f32 = lambda p_: _packed(self, "f32." + str(id(p_)), p_, torch.float32)  # noqa: E731
         # --- mlp.fc2: input gelu(u) ---
         hid = ops.gelu(u)
+        if drop is not None and drop["p_mlp"] > 0:
+            hid = ops.dropout(hid, drop["p_mlp"], *drop["kh"], out=hid)
         dw2 = ops.linear_wgrad(g2, hid)
         db2 = ops.colsum(g2)
         del hid
@@ -310,13 +374,14 @@ class Block(nn.Module):
 
     def forward(self, x):
         _check_input(x, "Block")
-        self.attn._check_train()
-        self.mlp._check_train()
-        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
-            raise NotImplementedError("Block: drop_path > 0 in training mode is not implemented on the B200 path yet")
+        if self.training and self.attn.attn_drop.p > 0:
+            raise NotImplementedError("Block: attn_drop > 0 in training mode is not implemented on the B200 path (the "
+                                      "mask would have to be generated inside the attention kernels); drop / drop_path are")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return _BlockFn.apply(x, self, *[p for p in self._param_list() if p is not None])
         B, N, C = x.shape
+        if self._is_stochastic():                               # train mode without autograd: masks still apply
+            return _from_bf16(self._forward_train(_to_bf16_2d(x), B, N)[0], x)
         return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N), x)
 
 

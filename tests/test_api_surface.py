@@ -61,8 +61,9 @@ def test_unsupported_configurations_raise():
         mt.Block(64, 1, norm_layer=nn.BatchNorm1d)
     with pytest.raises(NotImplementedError):
         mt.Data2Seq("graph", 768)
+    assert isinstance(mt.Data2Seq("text", 768).embed, data2seq.Text.TextFeaturePad)
     with pytest.raises(NotImplementedError):
-        mt.Data2Seq("text", 768)
+        data2seq.Text.get_text_embeddings(["a sentence"])        # the CLIP tower itself is not part of the path
     with pytest.raises(ValueError):
         mt.Data2Seq("smell", 768)
 

@@ -35,7 +35,19 @@ def main():
     loss.backward()
     params = [p for p in list(tok.parameters()) + list(enc.parameters()) if p.requires_grad]
     local = [p.grad.clone() for p in params]
-    n_coll = allreduce_gradients(params, world)
+    if "--ddp" in sys.argv and world > 1:
+        # same step through torch's DistributedDataParallel: parameters are inputs of the Block / tokenizer autograd
+        # nodes, so DDP's bucket hooks fire as each Block's backward finishes (all-reduce overlapped with the rest)
+        import torch.nn as nn
+        for p in params:
+            p.grad = None
+        ddp = nn.parallel.DistributedDataParallel(nn.Sequential(tok, enc), device_ids=[local_rank],
+                                                  bucket_cap_mb=8, broadcast_buffers=False)
+        y = ddp(images[lo:hi].to(dev))
+        (y.float().square().mean() * (hi - lo) / global_batch * world).backward()
+        n_coll = -1
+    else:
+        n_coll = allreduce_gradients(params, world)
     # independent check: gather every rank's local gradients and average them
     ok = True
     for p, lg in zip(params, local):
@@ -45,7 +57,9 @@ def main():
         else:
             bucket = [lg]
         mean = torch.stack(bucket).mean(0)
-        ok &= bool(torch.allclose(p.grad, mean, rtol=1e-4, atol=1e-6))
+        # (the DDP pass is a second backward: split-K / dQ atomics make it equal only to fp32 summation order)
+        tol = dict(rtol=2e-2, atol=1e-5) if "--ddp" in sys.argv else dict(rtol=1e-4, atol=1e-6)
+        ok &= bool(torch.allclose(p.grad, mean, **tol))
     nbytes = sum(p.numel() * p.element_size() for p in params)
     print(f"rank {rank}/{world}: finetune={finetune} grad bytes {nbytes / 1e6:.1f} MB shard [{lo},{hi}) loss {loss.item():.5f} collectives {n_coll} "
           f"grad_norm {params[0].grad.norm().item():.5f} allreduce_ok={ok}", flush=True)
