@@ -84,6 +84,12 @@ int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int N, int K, 
  * per output tile (0 = auto) and reduced with fp32 atomics (y is zeroed inside).  dW = dY^T X with x = dY^T, w = X^T.  */
 int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, int M, int N, int K, int splits, void* stream);
 
+/* Weight gradient of a Linear straight from the row-major activations: dw_f32[N_out, K_in] = dy[T, N_out]^T @ x[T, K_in]
+ * (bf16 operands consumed MN-major by tcgen05 — no transposed copies —, fp32 accumulation over the T tokens, split over
+ * `splits` CTA pairs per output tile (0 = auto) and reduced with fp32 atomics; dw is zeroed inside).
+ * Autograd of nn.Linear.weight in fine-tune mode (Audio/src/traintest.py:126-143) and of the conv tokenizers.       */
+int mt_gemm_bf16_wgrad(const void* dy, const void* x, float* dw_f32, int T, int N_out, int K_in, int splits, void* stream);
+
 /* ---- E2: LayerNorm over the last dim, fp32 statistics, biased variance -------------------------------------
  * y[M,d] (bf16) = (x - mean) * rsqrt(var + eps) * gamma + beta;  x bf16 or fp32 (x_dtype), gamma/beta fp32.
  * Replaces norm1 / norm2 = nn.LayerNorm(d) of Block (attention.py:46,50; eps 1e-5 per README.md:131).       */

@@ -16,7 +16,7 @@ LIB_PATH = _PKG / "lib" / "libmt_b200.so"
 MT_DT_BF16, MT_DT_F32, MT_DT_F16 = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
-    "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_gemm_bf16_ln", "mt_gemm_bf16_ex", "mt_gemm_bf16_splitk", "mt_row_stats",
+    "mt_version", "mt_last_error", "mt_device_ok", "mt_gemm_bf16", "mt_gemm_bf16_ln", "mt_gemm_bf16_ex", "mt_gemm_bf16_splitk", "mt_gemm_bf16_wgrad", "mt_row_stats",
     "mt_fold_layernorm", "mt_layernorm", "mt_layernorm_bwd", "mt_gelu", "mt_transpose_bf16", "mt_colsum", "mt_ln_fold_bwd", "mt_attention_fwd",
     "mt_attention_fwd_lse", "mt_attention_bwd_workspace_bytes", "mt_attention_bwd",
     "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_assemble_tokens", "mt_pool_layernorm", "mt_pool_layernorm_bwd",
@@ -70,6 +70,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_gemm_bf16_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(GemmOpts), c_void_p]
     lib.mt_gemm_bf16_splitk.restype = c_int
     lib.mt_gemm_bf16_splitk.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.mt_gemm_bf16_wgrad.restype = c_int
+    lib.mt_gemm_bf16_wgrad.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.mt_row_stats.restype = c_int
     lib.mt_row_stats.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p]
     lib.mt_fold_layernorm.restype = c_int

@@ -5,18 +5,27 @@
 // (Audio/src/models/ast_models.py:66-70): dX must flow through every Block.
 //
 // FlashAttention-2-style recomputation, Blackwell edition (sm_100a only, head_dim 64):
-//   work item = (batch, head, key tile j of 128 keys); loop over query tiles i of 128 rows:
+//   work item = (batch, head); loop over key tiles j of 128 keys, inside it over query tiles i of 128 rows:
 //     S^T  = K_j Q_i^T            tcgen05.mma 128x128x16   (TMEM cols   0..127)
 //     dP^T = V_j dO_i^T           tcgen05.mma 128x128x16   (TMEM cols 128..255)
 //     P^T  = exp2(S^T c - lse2_i) ;  dS^T = P^T (dP^T - delta_i) scale      (one key row per thread, fp32 registers)
 //     dV_j += P^T  dO_i           A = P^T  (smem, K-major),  B = dO_i (MN-major)     (TMEM cols 256..319)
 //     dK_j += dS^T Q_i            A = dS^T (smem, K-major),  B = Q_i  (MN-major)     (TMEM cols 320..383)
 //     dQ_i  = dS   K_j            A = dS^T read MN-major,     B = K_j  (MN-major)     (TMEM cols 384..447)
-//   dQ_i partials are added to an fp32 accumulator in HBM (red.global.add), dK_j / dV_j leave once per item.
+//   Two work decompositions (picked on the host by the number of (batch, head) pairs per SM):
+//    * owner: a CTA owns one (batch, head) at a time and walks its key tiles j, so the dQ_i partials of successive key
+//      tiles are combined by the same thread with plain fp32 loads / stores on an L2-resident scratch (first tile
+//      stores, middle tiles add, the last tile adds and writes bf16 into the q slot; the loads are issued before the
+//      wait on the MMAs) — no atomics, no zero-fill, no conversion pass, deterministic;
+//    * split: work item = (batch, head, key tile) for few, long sequences; dQ_i partials are added to a zero-filled
+//      fp32 accumulator with red.global.add and converted to bf16 by a small kernel afterwards.
+//   dK_j / dV_j leave once per key tile.
 //   lse2 = log2-sum-exp saved by the forward, delta_i = rowsum(dO_i * O_i) from a small pre-pass kernel.
-// Warps: 0-3 compute (warp = TMEM lane quarter), 4 = TMA loader, 5 = MMA issuer + TMEM allocator.
+// Warps: 0-7 compute (warp & 3 = TMEM lane quarter = 32 key rows, warp >> 2 = which 64-query half of the tile),
+//        8 = TMA loader, 9 = MMA issuer + TMEM allocator.
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
+#include <stdlib.h>
 
 namespace mt {
 
@@ -33,17 +42,20 @@ constexpr int kAbSmemBar = kAbSmemStat + 2 * 256 * 4;
 constexpr int kAbNumBars = 13;
 constexpr int kAbSmemTmemPtr = kAbSmemBar + kAbNumBars * 8;
 constexpr int kAbSmemBytes = kAbSmemTmemPtr + 16 + 1024;
-constexpr int kAbThreads = 192;
+constexpr int kAbThreads = 320;
+constexpr int kAbComputeWarps = 8;
 constexpr uint32_t kAbTmS = 0, kAbTmDP = 128, kAbTmDV = 256, kAbTmDK = 320, kAbTmDQ = 384;
 
 struct AttnBwdParams {
   int B, N, H;
   int num_t;         // ceil(N / 128): key tiles == query tiles
-  int num_items;     // B * H * num_t
+  int num_bh;        // B * H
+  int owner;         // 1: work item = (batch, head), key tiles walked inside; 0: work item = (batch, head, key tile)
+  int num_work;      // owner ? num_bh : num_bh * num_t
   float scale, scale_log2;
   const float* lse2;     // [B, H, N]
   const float* delta;    // [B, H, N]
-  float* dq_acc;         // [B, N, H, 64] fp32, zero-initialised
+  float* dq_acc;         // [B, N, H, 64] fp32: scratch (owner, num_t > 1) or zero-filled accumulator (split)
   __nv_bfloat16* dqkv;   // [B, N, 3, H, 64]
 };
 
@@ -113,29 +125,31 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                  kvacc_full = bar0 + 88, kvacc_empty = bar0 + 96;
   const uint32_t tmem_ptr_addr = smem_base + kAbSmemTmemPtr;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(qd_full(s), 1); mbar_init(qd_empty(s), 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
-    mbar_init(dq_empty, 4); mbar_init(kvacc_full, 1); mbar_init(kvacc_empty, 4);
+    mbar_init(s_full, 1); mbar_init(s_empty, kAbComputeWarps); mbar_init(p_full, kAbComputeWarps); mbar_init(pv_done, 1);
+    mbar_init(dq_empty, kAbComputeWarps); mbar_init(kvacc_full, 1); mbar_init(kvacc_empty, kAbComputeWarps);
     fence_mbar_init();
   }
   __syncwarp();
-  if (warp == 5) tmem_alloc<1>(tmem_ptr_addr, 512);
+  if (warp == 9) tmem_alloc<1>(tmem_ptr_addr, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + kAbSmemTmemPtr);
   const int H = p.H, NT = p.num_t;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =============================== TMA loader =================================
     if (lane == 0) {
       uint32_t n_item = 0, n_pair = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n_item) {
-        const int j = item % NT, bh = item / NT, h = bh % H, b = bh / H;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x)
+      for (int j = (p.owner ? 0 : w % NT), j1 = (p.owner ? NT : j + 1); j < j1; ++j, ++n_item) {
+        const int bh = p.owner ? w : w / NT;
+        const int h = bh % H, b = bh / H;
         mbar_wait(kv_empty, (n_item & 1u) ^ 1u);
         mbar_arrive_expect_tx(kv_full, 2 * kAbT);
         tma_load_4d(smem_base + kAbSmemK, &tm_qkv, kv_full, 0, H + h, j * 128, b, kEvictLast);
@@ -149,7 +163,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =============================== MMA issuer =================================
     if (lane == 0) {
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);    // K-major x K-major
@@ -162,7 +176,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const uint64_t ds_desc = make_smem_desc_sw128(smem_base + kAbSmemDS);
       // dS^T tile read as an MN-major A operand: the two 64-query column blocks are 16 KB apart (leading offset)
       const uint64_t ds_mn_desc = make_smem_desc_sw128(smem_base + kAbSmemDS, 1024, 2 * 8192);
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n_item) {
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x)
+      for (int j = (p.owner ? 0 : w % NT), j1 = (p.owner ? NT : j + 1); j < j1; ++j, ++n_item) {
         mbar_wait(kv_full, n_item & 1u);
         for (int i = 0; i < NT; ++i, ++n_pair) {
           const int st = int(n_pair & 1u);
@@ -203,7 +218,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     }
   } else {
     // =============================== compute warps ==============================
-    const int q4 = warp;                     // TMEM lane quarter
+    const int q4 = warp & 3;                 // TMEM lane quarter
+    const int hf = warp >> 2;                // which 64-query half of S^T / dP^T (and which half of the drains)
     const int r = 32 * q4 + lane;            // row inside the tile (key row for S^T/dP^T/dK/dV, query row for dQ)
     const uint32_t lane_off = uint32_t(32 * q4) << 16;
     const uint32_t row_smem = uint32_t(r * 128);
@@ -211,42 +227,60 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     float* stat = reinterpret_cast<float*>(smem_gen + kAbSmemStat);
     uint32_t n_item = 0, n_pair = 0;
     const float c = p.scale_log2, sc = p.scale;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n_item) {
-      const int j = item % NT, bh = item / NT, h = bh % H, b = bh / H;
+    // lse2 / delta of a query tile are fetched one (key tile, query tile) pair ahead by warps 0-3 (one query row per
+    // thread), so their global-load latency hides behind the previous pair (padded queries: +inf / 0 -> P = 0)
+    float pf_l = INFINITY, pf_d = 0.f;
+    auto prefetch_stats = [&](int bh_, int i_) {
+      pf_l = INFINITY;
+      pf_d = 0.f;
+      if (hf == 0 && bh_ < p.num_bh) {
+        const int h_ = bh_ % H, b_ = bh_ / H;
+        const int qi = i_ * 128 + r;
+        if (qi < p.N) {
+          const size_t off = (size_t(b_) * H + h_) * p.N + qi;
+          pf_l = p.lse2[off];
+          pf_d = p.delta[off];
+        }
+      }
+    };
+    prefetch_stats(p.owner ? int(blockIdx.x) : int(blockIdx.x) / NT, 0);
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x)
+    for (int j = (p.owner ? 0 : w % NT), j1 = (p.owner ? NT : j + 1); j < j1; ++j, ++n_item) {
+      const int bh = p.owner ? w : w / NT;
+      const int h = bh % H, b = bh / H;
       const bool key_ok = (j * 128 + r) < p.N;
       for (int i = 0; i < NT; ++i, ++n_pair) {
-        // stage lse2 / delta of this query tile (padded queries: +inf / 0 -> P = 0)
         float* st_l = stat + (n_pair & 1u) * 256;
-        {
-          const int qi = i * 128 + r;
-          const size_t off = (size_t(b) * H + h) * p.N + qi;
-          st_l[r] = (qi < p.N) ? p.lse2[off] : INFINITY;
-          st_l[128 + r] = (qi < p.N) ? p.delta[off] : 0.f;
+        if (hf == 0) {
+          st_l[r] = pf_l;
+          st_l[128 + r] = pf_d;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * kAbComputeWarps);
+        if (i + 1 < NT) prefetch_stats(bh, i + 1);
+        else if (j + 1 < j1) prefetch_stats(bh, 0);
+        else prefetch_stats((w + int(gridDim.x)) < p.num_work ? (p.owner ? w + int(gridDim.x) : (w + int(gridDim.x)) / NT)
+                                                               : p.num_bh, 0);
         mbar_wait(s_full, n_pair & 1u);
         tc_fence_after();
-#pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t s[64], dp[64];
-          tmem_ld_32x32b_x32_at<0>(tmem_base + lane_off + kAbTmS + uint32_t(64 * hf), s);
-          tmem_ld_32x32b_x32_at<32>(tmem_base + lane_off + kAbTmS + uint32_t(64 * hf + 32), s);
-          tmem_ld_32x32b_x32_at<0>(tmem_base + lane_off + kAbTmDP + uint32_t(64 * hf), dp);
-          tmem_ld_32x32b_x32_at<32>(tmem_base + lane_off + kAbTmDP + uint32_t(64 * hf + 32), dp);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {   // two 32-query slices of this warp's 64-query half
+          uint32_t s[32], dp[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmS + uint32_t(64 * hf + 32 * sub), s);
+          tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDP + uint32_t(64 * hf + 32 * sub), dp);
           tmem_wait_ld();
-          if (hf == 1) {
+          if (sub == 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty);
           }
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {   // eight 16-byte groups = 8 queries each
+          for (int g = 0; g < 4; ++g) {   // four 16-byte groups = 8 queries each
             uint32_t pp[4], dd[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c0 = 8 * g + 2 * e;
-              const float2 l2 = *reinterpret_cast<const float2*>(st_l + 64 * hf + c0);
-              const float2 dl = *reinterpret_cast<const float2*>(st_l + 128 + 64 * hf + c0);
+              const float2 l2 = *reinterpret_cast<const float2*>(st_l + 64 * hf + 32 * sub + c0);
+              const float2 dl = *reinterpret_cast<const float2*>(st_l + 128 + 64 * hf + 32 * sub + c0);
               float p0 = ex2f(fmaf(__uint_as_float(s[c0]), c, -l2.x));
               float p1 = ex2f(fmaf(__uint_as_float(s[c0 + 1]), c, -l2.y));
               if (!key_ok) { p0 = 0.f; p1 = 0.f; }
@@ -255,7 +289,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
               pp[e] = pack_bf16x2(p0, p1);
               dd[e] = pack_bf16x2(d0, d1);
             }
-            const uint32_t a = row_smem + uint32_t(hf * kAbT) + ((uint32_t(g) ^ swz) << 4);
+            const uint32_t a = row_smem + uint32_t(hf * kAbT) + ((uint32_t(4 * sub + g) ^ swz) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemP + a), "r"(pp[0]),
                          "r"(pp[1]), "r"(pp[2]), "r"(pp[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemDS + a), "r"(dd[0]),
@@ -265,68 +299,95 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
-        // ---- dQ partial of this (key tile, query tile) pair -> fp32 accumulator in HBM ----
+        // ---- dQ partial of this (key tile, query tile) pair (32 of the 64 columns per warp) ----
+        const int qi = i * 128 + r;
+        float* accp = p.dq_acc + ((size_t(b) * p.N + qi) * H + h) * 64 + 32 * hf;
+        float4 prev[8];
+        const bool rmw = p.owner && j > 0 && qi < p.N;
+        if (rmw) {   // owner mode: the partial of the previous key tiles, fetched while the MMAs of this pair run
+#pragma unroll
+          for (int e = 0; e < 8; ++e) prev[e] = reinterpret_cast<const float4*>(accp)[e];
+        }
         mbar_wait(pv_done, n_pair & 1u);   // also: P^T / dS^T smem may be overwritten from here on
         tc_fence_after();
         {
-          const int qi = i * 128 + r;
-          float* dst = p.dq_acc + ((size_t(b) * p.N + qi) * H + h) * 64;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDQ + uint32_t(32 * hh), o);
-            tmem_wait_ld();
-            if (qi < p.N) {
-#pragma unroll
-              for (int e = 0; e < 32; e += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32 * hh + e),
-                             "f"(__uint_as_float(o[e])), "f"(__uint_as_float(o[e + 1])),
-                             "f"(__uint_as_float(o[e + 2])), "f"(__uint_as_float(o[e + 3])) : "memory");
-            }
-          }
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDQ + uint32_t(32 * hf), o);
+          tmem_wait_ld();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(dq_empty);
-        }
-      }
-      // ---- dK_j, dV_j leave TMEM once per item ----
-      mbar_wait(kvacc_full, n_item & 1u);
-      tc_fence_after();
-      {
-        const int kv = j * 128 + r;
-        __nv_bfloat16* base = p.dqkv + ((size_t(b) * p.N + kv) * 3) * H * 64 + size_t(h) * 64;
+          if (qi < p.N) {
+            if (!p.owner) {
 #pragma unroll
-        for (int which = 0; which < 2; ++which) {   // 0: dK (slot 1), 1: dV (slot 2)
-          const uint32_t tcol = which == 0 ? kAbTmDK : kAbTmDV;
-          __nv_bfloat16* dst = base + size_t(which + 1) * H * 64;
+              for (int e = 0; e < 32; e += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(accp + e),
+                             "f"(__uint_as_float(o[e])), "f"(__uint_as_float(o[e + 1])),
+                             "f"(__uint_as_float(o[e + 2])), "f"(__uint_as_float(o[e + 3])) : "memory");
+            } else {
+              // the same thread owns these 32 values for every key tile of this (batch, head): plain read-modify-write
+              if (rmw) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_off + tcol + uint32_t(32 * hh), o);
-            tmem_wait_ld();
-            if (key_ok) {
+                for (int e = 0; e < 8; ++e) {
+                  o[4 * e + 0] = __float_as_uint(__uint_as_float(o[4 * e + 0]) + prev[e].x);
+                  o[4 * e + 1] = __float_as_uint(__uint_as_float(o[4 * e + 1]) + prev[e].y);
+                  o[4 * e + 2] = __float_as_uint(__uint_as_float(o[4 * e + 2]) + prev[e].z);
+                  o[4 * e + 3] = __float_as_uint(__uint_as_float(o[4 * e + 3]) + prev[e].w);
+                }
+              }
+              if (j + 1 < NT) {
 #pragma unroll
-              for (int e = 0; e < 32; e += 8) {
-                uint4 w;
-                w.x = pack_bf16x2(__uint_as_float(o[e]), __uint_as_float(o[e + 1]));
-                w.y = pack_bf16x2(__uint_as_float(o[e + 2]), __uint_as_float(o[e + 3]));
-                w.z = pack_bf16x2(__uint_as_float(o[e + 4]), __uint_as_float(o[e + 5]));
-                w.w = pack_bf16x2(__uint_as_float(o[e + 6]), __uint_as_float(o[e + 7]));
-                *reinterpret_cast<uint4*>(dst + 32 * hh + e) = w;
+                for (int e = 0; e < 8; ++e)
+                  reinterpret_cast<float4*>(accp)[e] = make_float4(__uint_as_float(o[4 * e]), __uint_as_float(o[4 * e + 1]),
+                                                                   __uint_as_float(o[4 * e + 2]), __uint_as_float(o[4 * e + 3]));
+              } else {
+                __nv_bfloat16* dst = p.dqkv + ((size_t(b) * p.N + qi) * 3) * H * 64 + size_t(h) * 64 + 32 * hf;   // q slot
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                  uint4 wv;
+                  wv.x = pack_bf16x2(__uint_as_float(o[e]), __uint_as_float(o[e + 1]));
+                  wv.y = pack_bf16x2(__uint_as_float(o[e + 2]), __uint_as_float(o[e + 3]));
+                  wv.z = pack_bf16x2(__uint_as_float(o[e + 4]), __uint_as_float(o[e + 5]));
+                  wv.w = pack_bf16x2(__uint_as_float(o[e + 6]), __uint_as_float(o[e + 7]));
+                  *reinterpret_cast<uint4*>(dst + e) = wv;
+                }
               }
             }
           }
         }
+      }
+      // ---- dK_j, dV_j leave TMEM once per item: warps 0-3 store dK (slot 1), warps 4-7 dV (slot 2) ----
+      mbar_wait(kvacc_full, n_item & 1u);
+      tc_fence_after();
+      {
+        const int kv = j * 128 + r;
+        __nv_bfloat16* dst = p.dqkv + ((size_t(b) * p.N + kv) * 3 + size_t(hf + 1)) * H * 64 + size_t(h) * 64;
+        const uint32_t tcol = hf == 0 ? kAbTmDK : kAbTmDV;
+        uint32_t o[64];
+        tmem_ld_32x32b_x32_at<0>(tmem_base + lane_off + tcol, o);
+        tmem_ld_32x32b_x32_at<32>(tmem_base + lane_off + tcol + 32u, o);
+        tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(kvacc_empty);
+        if (key_ok) {
+#pragma unroll
+          for (int e = 0; e < 64; e += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[e]), __uint_as_float(o[e + 1]));
+            w.y = pack_bf16x2(__uint_as_float(o[e + 2]), __uint_as_float(o[e + 3]));
+            w.z = pack_bf16x2(__uint_as_float(o[e + 4]), __uint_as_float(o[e + 5]));
+            w.w = pack_bf16x2(__uint_as_float(o[e + 6]), __uint_as_float(o[e + 7]));
+            *reinterpret_cast<uint4*>(dst + e) = w;
+          }
+        }
       }
     }
   }
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<1>(tmem_base, 512);
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
 }  // namespace mt
@@ -355,7 +416,6 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float* dq_acc = reinterpret_cast<float*>(workspace);
   float* delta = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((dq_bytes + 255) / 256) * 256);
-  MT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   {
     const long long rows = (long long)B * N;
     attn_bwd_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out),
@@ -381,17 +441,29 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
   AttnBwdParams p;
   p.B = B; p.N = N; p.H = H;
   p.num_t = ceil_div(N, 128);
-  p.num_items = B * H * p.num_t;
+  p.num_bh = B * H;
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  {
+    // owner mode needs enough (batch, head) pairs to balance the SMs (C2: 20.8 per SM, C3: 13.8); long sequences with
+    // few heads (C5: 3.5 per SM) split the key tiles over CTAs instead.  MT_B200_ATTN_BWD_OWNER=0|1 forces one (A/B runs).
+    static int forced = -2;
+    if (forced == -2) {
+      const char* e = getenv("MT_B200_ATTN_BWD_OWNER");
+      forced = (e && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
+    }
+    p.owner = forced >= 0 ? forced : (p.num_bh >= 8 * sms || p.num_t == 1) ? 1 : 0;
+  }
+  p.num_work = p.owner ? p.num_bh : p.num_bh * p.num_t;
+  if (!p.owner) MT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse2 = lse2;
   p.delta = delta;
   p.dq_acc = dq_acc;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  int sms = 0;
-  int rc = sm_count(&sms);
-  if (rc) return rc;
-  const int grid = p.num_items < sms ? p.num_items : sms;
+  const int grid = p.num_work < sms ? p.num_work : sms;
   {
     // the opt-in to > 48 KB of dynamic shared memory is per device (nn.DataParallel drives several from one process)
     static bool attr_set[64] = {false};
@@ -404,7 +476,7 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
   }
   attention_bwd_kernel<<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, p);
   MT_CHECK_CUDA(cudaGetLastError());
-  {
+  if (!p.owner) {
     const long long rows = (long long)B * N;
     long long blocks = (rows * H * 8 + 255) / 256;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;

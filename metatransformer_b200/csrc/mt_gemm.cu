@@ -71,6 +71,8 @@ struct GemmParams {
   float* out_row_sums;          // [M][2*num_n_tiles][2]: per-(row, 128-column slice) partial (sum, sum of squares) of
                                 // this GEMM's output, or nullptr (plain stores: deterministic, no zero-init)
   const float* colsum;          // [N] sum_k W'[n,k] (of the bf16-rounded folded weight) or nullptr
+  int mn_major;                 // 1: both operands are stored reduction-dim-major (A = dY[k, m], B = X[k, n]: the weight
+                                // gradient dW = dY^T X straight from the row-major activations, no transposed copies)
 };
 
 // gelu(x) = x * Phi(x) with the exact (erf) definition, nn.GELU() default.
@@ -192,7 +194,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          if constexpr (CG == 2) {
+          if (p.mn_major) {
+            // MN-major operand tiles: [64 reduction rows x 64 columns] boxes (128 B swizzle rows), 8 KB each; the
+            // 128-wide A / B slices of this CTA are two such boxes 8 KB apart (the descriptor's leading byte offset)
+            if constexpr (CG == 2) {
+              const uint32_t fb = full_leader_base + 8u * stage;
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg::kStageBytes);
+#pragma unroll
+              for (int blk = 0; blk < kBM / 64; ++blk)
+                tma_load_2d_cg2(sa + blk * 8192, &tm_a, fb, row_a + 64 * blk, kb * kBK, kEvictNormal);
+#pragma unroll
+              for (int blk = 0; blk < Cfg::kBRows / 64; ++blk)
+                tma_load_2d_cg2(sb + blk * 8192, &tm_b, fb, row_b + 64 * blk, kb * kBK, kEvictNormal);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+#pragma unroll
+              for (int blk = 0; blk < kBM / 64; ++blk)
+                tma_load_2d(sa + blk * 8192, &tm_a, full_bar(stage), row_a + 64 * blk, kb * kBK, kEvictNormal);
+#pragma unroll
+              for (int blk = 0; blk < Cfg::kBRows / 64; ++blk)
+                tma_load_2d(sb + blk * 8192, &tm_b, full_bar(stage), row_b + 64 * blk, kb * kBK, kEvictNormal);
+            }
+          } else if constexpr (CG == 2) {
             const uint32_t fb = full_leader_base + 8u * stage;
             // Only the leader arms its barrier, for the bytes of BOTH CTAs.  The peer's complete_tx may land before
             // the leader's expect_tx of the same phase (tx-count goes transiently negative, which is legal); it can
@@ -212,7 +235,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM * CG, kBN);
+      const uint32_t idesc = p.mn_major ? make_idesc_bf16(kBM * CG, kBN, 1, 1) : make_idesc_bf16(kBM * CG, kBN);
+      // K step of 16: K-major = 32 B inside the swizzle row; MN-major = 16 rows of 128 B
+      const uint64_t kstep = p.mn_major ? uint64_t(2048 >> 4) : uint64_t(2);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -227,12 +252,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::kABytes);
+          const uint64_t adesc = p.mn_major ? make_smem_desc_sw128(sa, 1024, 8192) : make_smem_desc_sw128(sa);
+          const uint64_t bdesc = p.mn_major ? make_smem_desc_sw128(sa + Cfg::kABytes, 1024, 8192)
+                                            : make_smem_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-            umma_f16_ss<CG>(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+            // advance 16 along K: +2 (32 B inside the 128B swizzle row) or +128 (16 rows) in the (addr >> 4) field
+            umma_f16_ss<CG>(d_tmem, adesc + kstep * uint64_t(k), bdesc + kstep * uint64_t(k), idesc,
                             (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           if constexpr (CG == 2) umma_commit_cg2_mc(empty_bar(stage), 0x3);
@@ -431,27 +457,42 @@ template <int CG>
 static int launch_gemm(const void* x, const void* w, const float* bias, const void* resid, int ldr, void* y, int M,
                        int N, int K, int act, const float* row_stats, const float* colsum, int ln_sums, float ln_eps,
                        float* out_row_sums, cudaStream_t stream, float* out_f32 = nullptr, int split_k = 1,
-                       int resid_period = 0) {
+                       int resid_period = 0, int mn_major = 0) {
   using Cfg = GemmCfg<CG>;
   CUtensorMap tm_a, tm_b, tm_y;
-  {
-    uint64_t dims[2] = {uint64_t(K), uint64_t(M)};
-    uint64_t strides[1] = {uint64_t(K) * 2};
-    uint32_t box[2] = {uint32_t(kBK), uint32_t(kBM)};
-    int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (mn_major) {
+    // x = dY [K tokens, M], w = X [K tokens, N], both row-major: 64 x 64 boxes with the output dimension innermost
+    uint32_t box[2] = {64u, uint32_t(kBK)};
+    uint64_t dims_a[2] = {uint64_t(M), uint64_t(K)};
+    uint64_t str_a[1] = {uint64_t(M) * 2};
+    int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims_a, str_a, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-  }
-  {
-    uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
-    uint64_t strides[1] = {uint64_t(K) * 2};
-    uint32_t box[2] = {uint32_t(kBK), uint32_t(Cfg::kBRows)};
-    int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint64_t dims_b[2] = {uint64_t(N), uint64_t(K)};
+    uint64_t str_b[1] = {uint64_t(N) * 2};
+    rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims_b, str_b, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  } else {
+    {
+      uint64_t dims[2] = {uint64_t(K), uint64_t(M)};
+      uint64_t strides[1] = {uint64_t(K) * 2};
+      uint32_t box[2] = {uint32_t(kBK), uint32_t(kBM)};
+      int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
+      uint64_t strides[1] = {uint64_t(K) * 2};
+      uint32_t box[2] = {uint32_t(kBK), uint32_t(Cfg::kBRows)};
+      int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   }
   {
     // (in split-K mode the bf16 output map is unused; it is encoded over the X operand only to keep the launch uniform)
-    uint64_t dims[2] = {uint64_t(out_f32 ? K : N), uint64_t(M)};
-    uint64_t strides[1] = {uint64_t(out_f32 ? K : N) * 2};
+    const uint64_t inner = out_f32 ? uint64_t(mn_major ? M : K) : uint64_t(N);
+    const uint64_t outer = out_f32 ? uint64_t(mn_major ? K : M) : uint64_t(M);
+    uint64_t dims[2] = {inner, outer};
+    uint64_t strides[1] = {inner * 2};
     uint32_t box[2] = {64u, 32u};
     int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_f32 ? x : y, dims, strides, box,
                          CU_TENSOR_MAP_SWIZZLE_128B);
@@ -462,6 +503,7 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   p.resid = reinterpret_cast<const __nv_bfloat16*>(resid);
   p.ldr = ldr;
   p.resid_period = resid_period;
+  p.mn_major = mn_major;
   p.M = M; p.N = N; p.K = K;
   p.act = act;
   p.row_stats = reinterpret_cast<const float2*>(row_stats);
@@ -596,4 +638,28 @@ extern "C" int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, i
   }
   MT_CHECK_CUDA(cudaMemsetAsync(y_f32, 0, size_t(M) * N * sizeof(float), s));
   return launch_gemm<2>(x, w, nullptr, nullptr, N, nullptr, M, N, K, 0, nullptr, nullptr, 0, 0.f, nullptr, s, y_f32, splits);
+}
+
+// dW_f32[N_out, K_in] = dY[T, N_out]^T @ X[T, K_in]: the weight gradient read straight from the two row-major activation
+// matrices (MN-major tcgen05 operands: no transposed copies), reduction over the T tokens split over CTA pairs.
+extern "C" int mt_gemm_bf16_wgrad(const void* dy, const void* x, float* dw_f32, int T, int N_out, int K_in, int splits,
+                                  void* stream) {
+  using namespace mt;
+  MT_REQUIRE(dy && x && dw_f32, MT_ERR_BAD_SHAPE, "mt_gemm_bf16_wgrad: null pointer");
+  MT_REQUIRE(T > 0 && N_out > 0 && K_in > 0 && N_out % 8 == 0 && K_in % 8 == 0, MT_ERR_BAD_SHAPE,
+             "mt_gemm_bf16_wgrad: need T > 0 and N_out, K_in positive multiples of 8 (got %d,%d,%d)", T, N_out, K_in);
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw_f32)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_gemm_bf16_wgrad: pointers must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (splits <= 0) {
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
+    const int tiles = ceil_div(N_out, 2 * kBM) * ceil_div(K_in, kBN);
+    splits = ceil_div(sms, tiles);
+    if (splits < 1) splits = 1;
+  }
+  MT_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, size_t(N_out) * K_in * sizeof(float), s));
+  return launch_gemm<2>(dy, x, nullptr, nullptr, K_in, nullptr, N_out, K_in, T, 0, nullptr, nullptr, 0, 0.f, nullptr, s,
+                        dw_f32, splits, 0, 1);
 }

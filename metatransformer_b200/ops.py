@@ -268,15 +268,24 @@ def ln_fold_bwd(dw_folded: torch.Tensor, weight: torch.Tensor, gamma: torch.Tens
     return dw, dg, db
 
 
-def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, splits: int = 0) -> torch.Tensor:
-    """dW [N,K] fp32 = dy[M,N]^T @ x[M,K]: transposed bf16 copies + the split-K tcgen05 GEMM (fp32 accumulation over M)."""
-    dyt, xt = transpose(dy), transpose(x)          # [N, Mp], [K, Mp]
-    N, Mp = dyt.shape
-    K = xt.shape[0]
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, splits: int = 0, via_transpose: bool = False) -> torch.Tensor:
+    """dW [N,K] fp32 = dy[M,N]^T @ x[M,K] (fp32 accumulation over the M tokens, split-K tcgen05 GEMM).  Default: both
+    operands are read MN-major straight from the row-major activations (mt_gemm_bf16_wgrad); via_transpose=True is the
+    older form on transposed bf16 copies (kept as a cross-check)."""
+    _require_cuda(dy, x)
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or dy.shape[0] != x.shape[0]:
+        raise ValueError("linear_wgrad: dy [M,N] and x [M,K] must be bf16 with the same M")
+    M, N = dy.shape
+    K = x.shape[1]
     dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
     with torch.cuda.device(dy.device):
-        check(_lib.load().mt_gemm_bf16_splitk(dyt.data_ptr(), xt.data_ptr(), dw.data_ptr(), N, K, Mp, splits, _stream()),
-              "mt_gemm_bf16_splitk")
+        if via_transpose:
+            dyt, xt = transpose(dy), transpose(x)          # [N, Mp], [K, Mp]
+            check(_lib.load().mt_gemm_bf16_splitk(dyt.data_ptr(), xt.data_ptr(), dw.data_ptr(), N, K, dyt.shape[1], splits,
+                                                  _stream()), "mt_gemm_bf16_splitk")
+        else:
+            check(_lib.load().mt_gemm_bf16_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), M, N, K, splits, _stream()),
+                  "mt_gemm_bf16_wgrad")
     return dw
 
 

@@ -145,13 +145,16 @@ def test_trainable_tokenizer_under_frozen_encoder(mt):
     assert all(p.grad is None for p in enc.parameters())
 
 
-@pytest.mark.parametrize("M,N,K,splits", [(1000, 96, 200, 0), (50176, 768, 768, 0), (4096, 3072, 768, 7), (333, 64, 64, 1)])
-def test_splitk_weight_gradient_gemm(mt, M, N, K, splits):
-    """dW = dY^T X in fp32 through transposed copies + the split-K GEMM (fp32 atomics)"""
+@pytest.mark.parametrize("via_transpose", [False, True])
+@pytest.mark.parametrize("M,N,K,splits", [(1000, 96, 200, 0), (50176, 768, 768, 0), (4096, 3072, 768, 7), (333, 64, 64, 1),
+                                          (197, 8, 3072, 0), (2, 520, 72, 3)])
+def test_splitk_weight_gradient_gemm(mt, M, N, K, splits, via_transpose):
+    """dW = dY^T X in fp32 by the split-K GEMM (fp32 atomics): MN-major operands straight from the row-major
+    activations (default) and the older form on transposed copies."""
     g = torch.Generator().manual_seed(M + N)
     dy = _bf16_round(torch.randn(M, N, generator=g) * 0.1)
     x = _bf16_round(torch.randn(M, K, generator=g))
     ref = dy.double().t() @ x.double()
-    dw = mt.ops.linear_wgrad(dy.cuda().bfloat16(), x.cuda().bfloat16(), splits)
+    dw = mt.ops.linear_wgrad(dy.cuda().bfloat16(), x.cuda().bfloat16(), splits, via_transpose=via_transpose)
     assert dw.dtype == torch.float32 and dw.shape == (N, K)
-    _assert_close(dw, ref, rel=1e-4, mx=1e-4, what=f"split-K wgrad {M}x{N}x{K}")
+    _assert_close(dw, ref, rel=1e-4, mx=1e-4, what=f"split-K wgrad {M}x{N}x{K} via_transpose={via_transpose}")

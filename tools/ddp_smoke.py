@@ -21,6 +21,11 @@ from metatransformer_b200.distributed import allreduce_gradients, init_process_g
 def main():
     rank, local_rank, world = init_process_group("nccl")
     dev = torch.device("cuda", local_rank)
+    if "--ddp" in sys.argv and not dist.is_initialized():     # single-process debugging of the DDP wrapper
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
     torch.manual_seed(0)                                  # identical weights on every rank
     finetune = "--finetune" in sys.argv      # encoder weights trainable too: 2 x 7.1 M parameters -> several buckets
     enc = mt.build_encoder("base", depth=2).to(dev)
@@ -35,7 +40,7 @@ def main():
     loss.backward()
     params = [p for p in list(tok.parameters()) + list(enc.parameters()) if p.requires_grad]
     local = [p.grad.clone() for p in params]
-    if "--ddp" in sys.argv and world > 1:
+    if "--ddp" in sys.argv:
         # same step through torch's DistributedDataParallel: parameters are inputs of the Block / tokenizer autograd
         # nodes, so DDP's bucket hooks fire as each Block's backward finishes (all-reduce overlapped with the rest)
         import torch.nn as nn
@@ -63,7 +68,7 @@ def main():
     nbytes = sum(p.numel() * p.element_size() for p in params)
     print(f"rank {rank}/{world}: finetune={finetune} grad bytes {nbytes / 1e6:.1f} MB shard [{lo},{hi}) loss {loss.item():.5f} collectives {n_coll} "
           f"grad_norm {params[0].grad.norm().item():.5f} allreduce_ok={ok}", flush=True)
-    if world > 1:
+    if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
     if not ok:

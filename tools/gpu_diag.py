@@ -204,6 +204,33 @@ def group_perf():
     print(f"[perf] layernorm M={M} d=768: {ms:.4f} ms  {M * 768 * 4 / ms / 1e6:.1f} GB/s", flush=True)
 
 
+def group_abw():
+    """attention backward only: the four BASELINE shapes, 30 timed iterations each (MT_B200_ATTN_BWD_OWNER=0|1 for A/B)."""
+    import torch
+    dev = torch.device("cuda")
+    from metatransformer_b200 import ops
+    mode = os.environ.get("MT_B200_ATTN_BWD_OWNER", "auto")
+    iters = int(os.environ.get("ABW_ITERS", "30"))
+    shapes = [(256, 196, 12), (128, 256, 16), (64, 512, 12), (32, 1568, 16)]
+    if "ABW_ONLY" in os.environ:
+        shapes = [shapes[int(os.environ["ABW_ONLY"])]]
+    for (B, N, H) in shapes:
+        qkv = torch.randn(B, N, 3 * H * 64, device=dev).bfloat16()
+        o, lse = ops.attention_lse(qkv, H)
+        do = torch.randn_like(o)
+        for _ in range(3):
+            ops.attention_bwd(qkv, o, do, lse, H)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            ops.attention_bwd(qkv, o, do, lse, H)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"[abw owner={mode}] B={B} N={N} H={H}: {ms:.4f} ms  {10.0 * B * H * N * N * 64 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def group_prof():
     """tiny launch set for ncu: fc2-shaped GEMM, cg=1 then cg=2, plus attention and layernorm"""
     import torch
@@ -272,7 +299,7 @@ def group_prof_layer():
     torch.cuda.synchronize()
 
 
-GROUPS = {"prof": group_prof, "prof_layer": group_prof_layer, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+GROUPS = {"abw": group_abw, "prof": group_prof, "prof_layer": group_prof_layer, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
 
 
 def main():
