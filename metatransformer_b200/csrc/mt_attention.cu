@@ -283,8 +283,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             m_tile = fmaxf(m_tile, v);
           }
         }
-        const float m_new = fmaxf(m_run, m_tile);
-        const float alpha = ex2_approx((m_run - m_new) * c);  // 0 on the first tile (m_run = -inf)
+        // Lazy rescaling: the running maximum is only advanced (and O_t rescaled) when some row of this warp saw its
+        // maximum grow by more than 2^kLazyLog2; otherwise the stale maximum keeps being the reference — P may then
+        // exceed 1 (by at most 2^kLazyLog2, harmless in fp32 / bf16) and O / l at the end is unchanged mathematically.
+        // With 128-key tiles the maximum almost never jumps that far after the first tile, so the TMEM round trip
+        // of O_t disappears from the critical path.
+        constexpr float kLazyLog2 = 8.0f;
+        const bool grow = (j > 0) && __any_sync(0xffffffffu, (m_tile - m_run) * c > kLazyLog2);
+        const float m_new = (j == 0) ? m_tile : (grow ? fmaxf(m_run, m_tile) : m_run);
+        const float alpha = grow ? ex2_approx((m_run - m_new) * c) : 1.0f;
         const float mc = m_new * c;
         m_run = m_new;
 
@@ -294,17 +301,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           mbar_wait(o_done(t), n_od & 1u);
           ++n_od;
           tc_fence_after();
-          // rescale the running output by alpha
+          if (grow) {
+            // rescale the running output by alpha
+            const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(to + uint32_t(32 * hh), o);
-            tmem_wait_ld();
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(to + uint32_t(32 * hh), o);
+              tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(to + uint32_t(32 * hh), o);
+              for (int i = 0; i < 32; i += 2) {
+                float a0, a1;
+                unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), a0, a1);
+                o[i] = __float_as_uint(a0);
+                o[i + 1] = __float_as_uint(a1);
+              }
+              tmem_st_32x32b_x32(to + uint32_t(32 * hh), o);
+            }
+            tmem_wait_st();
           }
-          tmem_wait_st();
         }
         if (store_pending) {
           // the previous item's output tile was staged in this warp's rows of P_t
@@ -313,7 +328,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           store_pending = false;
         }
         // ---- P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V) ----
-        float l_tile = 0.f;
+        uint64_t l2 = pack_f32x2(0.f, 0.f);   // two partial row sums (even / odd keys), packed fp32x2 adds
+        const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           if (ch < nfull) {
@@ -322,9 +338,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
               uint32_t pk[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float e0 = ex2_approx(fmaf(__uint_as_float(s[32 * ch + 8 * g + 2 * i]), c, -mc));
-                const float e1 = ex2_approx(fmaf(__uint_as_float(s[32 * ch + 8 * g + 2 * i + 1]), c, -mc));
-                l_tile += e0 + e1;
+                float a0, a1;
+                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[32 * ch + 8 * g + 2 * i]),
+                                                  __uint_as_float(s[32 * ch + 8 * g + 2 * i + 1])), c2, nmc2), a0, a1);
+                const float e0 = ex2_approx(a0);
+                const float e1 = ex2_approx(a1);
+                l2 = add_f32x2(l2, pack_f32x2(e0, e1));
                 pk[i] = pack_bf16x2(e0, e1);
               }
               const uint32_t chunk16 = uint32_t((ch & 1) * 4 + g);
@@ -341,9 +360,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             uint32_t pk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float e0 = ex2_approx(fmaf(__uint_as_float(s[96 + 8 * g + 2 * i]), c, -mc));   // exp2(-inf) = 0
-              const float e1 = ex2_approx(fmaf(__uint_as_float(s[96 + 8 * g + 2 * i + 1]), c, -mc));
-              l_tile += e0 + e1;
+              float a0, a1;
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[96 + 8 * g + 2 * i]), __uint_as_float(s[96 + 8 * g + 2 * i + 1])),
+                                     c2, nmc2), a0, a1);
+              const float e0 = ex2_approx(a0);   // exp2(-inf) = 0
+              const float e1 = ex2_approx(a1);
+              l2 = add_f32x2(l2, pack_f32x2(e0, e1));
               pk[i] = pack_bf16x2(e0, e1);
             }
             const uint32_t chunk16 = uint32_t((nfull & 1) * 4 + g);
@@ -353,7 +375,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
                          : "memory");
           }
         }
-        l_run = fmaf(l_run, alpha, l_tile);
+        float l_lo, l_hi;
+        unpack_f32x2(l2, l_lo, l_hi);
+        l_run = fmaf(l_run, alpha, l_lo + l_hi);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -365,6 +389,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       ++n_od;
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
+      const uint64_t inv_l2 = pack_f32x2(inv_l, inv_l);
       {
         const int qrow = qp * 256 + t * 128 + r_in_tile;
         if (p.lse2 != nullptr && qrow < p.N) p.lse2[(size_t(b) * H + h) * p.N + qrow] = fmaf(m_run, c, log2f(l_run));
@@ -376,8 +401,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         tmem_ld_32x32b_x32(to + uint32_t(32 * hh), o);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          ob[(32 * hh + i) >> 1] = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+        for (int i = 0; i < 32; i += 2) {
+          float a0, a1;
+          unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), inv_l2), a0, a1);
+          ob[(32 * hh + i) >> 1] = pack_bf16x2(a0, a1);
+        }
       }
       tc_fence_before();
 #pragma unroll

@@ -616,6 +616,25 @@ extern "C" int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int
                     o->cta_group, stream, o->ln_stats_are_sums, o->ln_eps, o->out_row_sums, o->residual_period);
 }
 
+// Number of K splits for the fp32-accumulating (weight-gradient) GEMM: (output tiles x splits) should fill whole waves of
+// CTA pairs — e.g. 9 tiles (768 x 768) x 8 = 72 items on 74 pairs, 36 tiles x 4 = 144 items = 2 waves at 97 % — while
+// keeping every split at least 8 k-blocks long and the number of atomic passes over the output low.
+static int auto_splits(int tiles, int num_kb, int sms) {
+  const int pairs = sms / 2 > 0 ? sms / 2 : 1;
+  int best = 1;
+  double best_score = -1.0;
+  for (int sp = 1; sp <= 32; ++sp) {
+    if (sp > 1 && num_kb / sp < 8) break;
+    const int items = tiles * sp;
+    const int waves = (items + pairs - 1) / pairs;
+    double score = double(items) / double(waves * pairs);     // wave efficiency
+    if (waves < 2) score *= 0.97;                               // a single wave cannot hide its own prologue
+    score -= 0.004 * sp;                                        // every split is one more atomic pass over dW
+    if (score > best_score) { best_score = score; best = sp; }
+  }
+  return best;
+}
+
 // y_f32[M,N] += x[M,K] @ w[N,K]^T with the K range split over `splits` CTAs per output tile (fp32 atomics).
 // Meant for weight gradients dW = dY^T X (x = dY^T, w = X^T): a handful of output tiles and K = number of tokens.
 extern "C" int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, int M, int N, int K, int splits,
@@ -632,9 +651,7 @@ extern "C" int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, i
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc) return rc;
-    const int tiles = ceil_div(M, 2 * kBM) * ceil_div(N, kBN);
-    splits = ceil_div(sms, tiles);
-    if (splits < 1) splits = 1;
+    splits = auto_splits(ceil_div(M, 2 * kBM) * ceil_div(N, kBN), ceil_div(K, kBK), sms);
   }
   MT_CHECK_CUDA(cudaMemsetAsync(y_f32, 0, size_t(M) * N * sizeof(float), s));
   return launch_gemm<2>(x, w, nullptr, nullptr, N, nullptr, M, N, K, 0, nullptr, nullptr, 0, 0.f, nullptr, s, y_f32, splits);
@@ -655,9 +672,7 @@ extern "C" int mt_gemm_bf16_wgrad(const void* dy, const void* x, float* dw_f32, 
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc) return rc;
-    const int tiles = ceil_div(N_out, 2 * kBM) * ceil_div(K_in, kBN);
-    splits = ceil_div(sms, tiles);
-    if (splits < 1) splits = 1;
+    splits = auto_splits(ceil_div(N_out, 2 * kBM) * ceil_div(K_in, kBN), ceil_div(T, kBK), sms);
   }
   MT_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, size_t(N_out) * K_in * sizeof(float), s));
   return launch_gemm<2>(dy, x, nullptr, nullptr, K_in, nullptr, N_out, K_in, T, 0, nullptr, nullptr, 0, 0.f, nullptr, s,
