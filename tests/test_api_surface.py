@@ -95,3 +95,34 @@ def test_compat_shim_resolves_reference_imports():
         from timm.models.vision_transformer import Block    # README.md:116
         assert Block is mt.Block
     compat.install()                                        # idempotent
+
+
+def test_classifier_head_surface_and_no_cpu_fallback():
+    head = mt.ClassifierHead(64, 10, pool="cls_dist")
+    assert sorted(k for k, _ in head.named_parameters()) == ["head.bias", "head.weight", "norm.bias", "norm.weight"]
+    assert head.head.weight.shape == (10, 64) and head.norm.eps == 1e-5
+    feat = mt.ClassifierHead(64, 0, pool="mean")
+    assert isinstance(feat.head, nn.Identity)
+    with pytest.raises(ValueError):
+        mt.ClassifierHead(64, 10, pool="max")
+    with pytest.raises(NotImplementedError):
+        mt.ClassifierHead(64, 10, norm_layer=nn.BatchNorm1d)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        head(torch.zeros(2, 5, 64))
+
+
+def test_tokenizer_forward_signatures_accept_pos_embed_and_prefix_tokens():
+    import inspect
+    for mod in (data2seq.Image, data2seq.Acoustic, data2seq.Video):
+        params = inspect.signature(mod.PatchEmbed.forward).parameters
+        assert "pos_embed" in params and "prefix_tokens" in params
+        assert params["pos_embed"].default is None and params["prefix_tokens"].default is None   # reference call unchanged
+    with pytest.raises(RuntimeError, match="no CPU"):
+        data2seq.Text.zero_padding(torch.zeros(2, 512), 768)
+
+
+def test_block_dropout_configuration_is_accepted_and_attn_drop_documented():
+    blk = mt.Block(64, 2, qkv_bias=True, drop=0.1, attn_drop=0.0, drop_path=0.2)
+    assert blk.attn.proj_drop.p == 0.1 and blk.mlp.drop.p == 0.1 and blk.drop_path.drop_prob == 0.2
+    assert blk._is_stochastic() and not blk.eval()._is_stochastic()
+    assert mt.Block(64, 2)._is_stochastic() is False
