@@ -30,40 +30,81 @@
 namespace mt {
 
 constexpr int kAbT = 128 * 64 * 2;          // bytes of one 128 x 64 bf16 tile
-constexpr int kAbSmemK = 0;
-constexpr int kAbSmemV = kAbSmemK + kAbT;
-constexpr int kAbSmemQ = kAbSmemV + kAbT;   // 2 stages
+constexpr int kAbSmemK = 0;                 // 2 slots (key tiles of successive work items)
+constexpr int kAbSmemV = kAbSmemK + 2 * kAbT;
+constexpr int kAbSmemQ = kAbSmemV + 2 * kAbT;   // 2 stages
 constexpr int kAbSmemDO = kAbSmemQ + 2 * kAbT;
 constexpr int kAbSmemP = kAbSmemDO + 2 * kAbT;   // P^T: 2 chunks of 64 queries
 constexpr int kAbSmemDS = kAbSmemP + 2 * kAbT;   // dS^T
 constexpr int kAbSmemStat = kAbSmemDS + 2 * kAbT;  // 2 x (128 lse2 + 128 delta) floats
 constexpr int kAbSmemBar = kAbSmemStat + 2 * 256 * 4;
-// barriers: kv_full kv_empty qd_full[2] qd_empty[2] s_full s_empty p_full pv_done dq_empty kvacc_full kvacc_empty
-constexpr int kAbNumBars = 13;
+// barriers: kv_full[2] kv_empty[2] qd_full[2] qd_empty[2] s_full s_empty p_full pv_done
+constexpr int kAbNumBars = 12;
 constexpr int kAbSmemTmemPtr = kAbSmemBar + kAbNumBars * 8;
 constexpr int kAbSmemBytes = kAbSmemTmemPtr + 16 + 1024;
 constexpr int kAbThreads = 320;
 constexpr int kAbComputeWarps = 8;
-constexpr uint32_t kAbTmS = 0, kAbTmDP = 128, kAbTmDV = 256, kAbTmDK = 320, kAbTmDQ = 384;
+constexpr uint32_t kAbTmS = 0, kAbTmDP = 128, kAbTmDV = 256, kAbTmDK = 320, kAbTmDQ = 384;   // dQ: 384 (+64 resident #2)
 
 struct AttnBwdParams {
   int B, N, H;
   int num_t;         // ceil(N / 128): key tiles == query tiles
   int num_bh;        // B * H
   int owner;         // 1: work item = (batch, head), key tiles walked inside; 0: work item = (batch, head, key tile)
+  int resident;      // owner && num_t <= 2: dQ_i stays in TMEM across the key tiles (no scratch at all)
   int num_work;      // owner ? num_bh : num_bh * num_t
   float scale, scale_log2;
   const float* lse2;     // [B, H, N]
   const float* delta;    // [B, H, N]
-  float* dq_acc;         // [B, N, H, 64] fp32: scratch (owner, num_t > 1) or zero-filled accumulator (split)
+  float* dq_acc;         // [B, N, H, 64] fp32: scratch (owner, num_t > 2) or zero-filled accumulator (split)
   __nv_bfloat16* dqkv;   // [B, N, 3, H, 64]
 };
+
+// 32-byte store of 16 bf16 values held as fp32 bit patterns in o[0..15] (full-sector writes from scattered rows)
+MT_DEVINL void st_global_bf16x16(__nv_bfloat16* dst, const uint32_t* o) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst),
+               "r"(pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1]))),
+               "r"(pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3]))),
+               "r"(pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5]))),
+               "r"(pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7]))),
+               "r"(pack_bf16x2(__uint_as_float(o[8]), __uint_as_float(o[9]))),
+               "r"(pack_bf16x2(__uint_as_float(o[10]), __uint_as_float(o[11]))),
+               "r"(pack_bf16x2(__uint_as_float(o[12]), __uint_as_float(o[13]))),
+               "r"(pack_bf16x2(__uint_as_float(o[14]), __uint_as_float(o[15])))
+               : "memory");
+}
 
 MT_DEVINL float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// The sequence of (work item w, key tile j, query tile i) pairs one CTA walks; all three warp roles step through it
+// with the same function, so their barrier phases stay in lock step.
+struct AbPair {
+  int w, j, i;
+  bool valid;
+};
+MT_DEVINL AbPair ab_first(const AttnBwdParams& p, int NT) {
+  AbPair s;
+  s.w = int(blockIdx.x);
+  s.valid = s.w < p.num_work;
+  s.j = p.owner ? 0 : s.w % NT;
+  s.i = 0;
+  return s;
+}
+MT_DEVINL AbPair ab_next(AbPair s, const AttnBwdParams& p, int NT) {
+  if (++s.i < NT) return s;
+  s.i = 0;
+  const int j1 = p.owner ? NT : (s.w % NT) + 1;
+  if (++s.j < j1) return s;
+  s.w += int(gridDim.x);
+  s.valid = s.w < p.num_work;
+  s.j = p.owner ? 0 : (s.valid ? s.w % NT : 0);
+  return s;
+}
+MT_DEVINL int ab_bh(const AbPair& s, const AttnBwdParams& p, int NT) { return p.owner ? s.w : s.w / NT; }
 
 // delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]   (one warp per (b,n) row; lane pairs cover one head)
 __global__ void __launch_bounds__(256) attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o,
@@ -118,20 +159,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_base + kAbSmemBar;
-  const uint32_t kv_full = bar0, kv_empty = bar0 + 8;
-  auto qd_full = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto qd_empty = [&](int s) { return bar0 + 8u * (4 + s); };
-  const uint32_t s_full = bar0 + 48, s_empty = bar0 + 56, p_full = bar0 + 64, pv_done = bar0 + 72, dq_empty = bar0 + 80,
-                 kvacc_full = bar0 + 88, kvacc_empty = bar0 + 96;
+  auto kv_full = [&](int s) { return bar0 + 8u * s; };
+  auto kv_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto qd_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto qd_empty = [&](int s) { return bar0 + 8u * (6 + s); };
+  const uint32_t s_full = bar0 + 64, s_empty = bar0 + 72, p_full = bar0 + 80, pv_done = bar0 + 88;
   const uint32_t tmem_ptr_addr = smem_base + kAbSmemTmemPtr;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
-    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(qd_full(s), 1); mbar_init(qd_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1);
+      mbar_init(qd_full(s), 1); mbar_init(qd_empty(s), 1);
+    }
     mbar_init(s_full, 1); mbar_init(s_empty, kAbComputeWarps); mbar_init(p_full, kAbComputeWarps); mbar_init(pv_done, 1);
-    mbar_init(dq_empty, kAbComputeWarps); mbar_init(kvacc_full, 1); mbar_init(kvacc_empty, kAbComputeWarps);
     fence_mbar_init();
   }
   __syncwarp();
@@ -144,76 +186,107 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   if (warp == 8) {
     // =============================== TMA loader =================================
+    // K_j / V_j: two slots, so the tiles of the next work item arrive while the current one is being consumed;
+    // Q_i / dO_i: two stages.
     if (lane == 0) {
       uint32_t n_item = 0, n_pair = 0;
-      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x)
-      for (int j = (p.owner ? 0 : w % NT), j1 = (p.owner ? NT : j + 1); j < j1; ++j, ++n_item) {
-        const int bh = p.owner ? w : w / NT;
-        const int h = bh % H, b = bh / H;
-        mbar_wait(kv_empty, (n_item & 1u) ^ 1u);
-        mbar_arrive_expect_tx(kv_full, 2 * kAbT);
-        tma_load_4d(smem_base + kAbSmemK, &tm_qkv, kv_full, 0, H + h, j * 128, b, kEvictLast);
-        tma_load_4d(smem_base + kAbSmemV, &tm_qkv, kv_full, 0, 2 * H + h, j * 128, b, kEvictLast);
-        for (int i = 0; i < NT; ++i, ++n_pair) {
-          const int st = int(n_pair & 1u);
-          mbar_wait(qd_empty(st), ((n_pair >> 1) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(qd_full(st), 2 * kAbT);
-          tma_load_4d(smem_base + kAbSmemQ + st * kAbT, &tm_qkv, qd_full(st), 0, h, i * 128, b, kEvictLast);
-          tma_load_4d(smem_base + kAbSmemDO + st * kAbT, &tm_do, qd_full(st), 0, h, i * 128, b, kEvictLast);
+      for (AbPair cur = ab_first(p, NT); cur.valid; cur = ab_next(cur, p, NT), ++n_pair) {
+        const int bh = ab_bh(cur, p, NT), h = bh % H, b = bh / H;
+        if (cur.i == 0) {
+          const int sl = int(n_item & 1u);
+          mbar_wait(kv_empty(sl), ((n_item >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(kv_full(sl), 2 * kAbT);
+          tma_load_4d(smem_base + kAbSmemK + sl * kAbT, &tm_qkv, kv_full(sl), 0, H + h, cur.j * 128, b, kEvictLast);
+          tma_load_4d(smem_base + kAbSmemV + sl * kAbT, &tm_qkv, kv_full(sl), 0, 2 * H + h, cur.j * 128, b, kEvictLast);
+          ++n_item;
         }
+        const int st = int(n_pair & 1u);
+        mbar_wait(qd_empty(st), ((n_pair >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(qd_full(st), 2 * kAbT);
+        tma_load_4d(smem_base + kAbSmemQ + st * kAbT, &tm_qkv, qd_full(st), 0, h, cur.i * 128, b, kEvictLast);
+        tma_load_4d(smem_base + kAbSmemDO + st * kAbT, &tm_do, qd_full(st), 0, h, cur.i * 128, b, kEvictLast);
       }
     }
   } else if (warp == 9) {
     // =============================== MMA issuer =================================
+    // Software pipeline: S^T / dP^T of pair n+1 are issued as soon as the compute warps have pulled pair n's scores
+    // into registers (s_empty), i.e. BEFORE the dV / dK / dQ MMAs of pair n (which need P^T / dS^T of pair n):
+    // the tensor core computes the next scores while the compute warps are busy with the current ones.
     if (lane == 0) {
       constexpr uint32_t id_s = make_idesc_bf16(128, 128, 0, 0);    // K-major x K-major
       constexpr uint32_t id_kv = make_idesc_bf16(128, 64, 0, 1);    // A K-major (P^T / dS^T), B MN-major (dO / Q)
       constexpr uint32_t id_dq = make_idesc_bf16(128, 64, 1, 1);    // A = dS read MN-major, B = K MN-major
-      uint32_t n_item = 0, n_pair = 0;
-      const uint64_t k_desc = make_smem_desc_sw128(smem_base + kAbSmemK);
-      const uint64_t v_desc = make_smem_desc_sw128(smem_base + kAbSmemV);
       const uint64_t p_desc = make_smem_desc_sw128(smem_base + kAbSmemP);
       const uint64_t ds_desc = make_smem_desc_sw128(smem_base + kAbSmemDS);
       // dS^T tile read as an MN-major A operand: the two 64-query column blocks are 16 KB apart (leading offset)
       const uint64_t ds_mn_desc = make_smem_desc_sw128(smem_base + kAbSmemDS, 1024, 2 * 8192);
-      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x)
-      for (int j = (p.owner ? 0 : w % NT), j1 = (p.owner ? NT : j + 1); j < j1; ++j, ++n_item) {
-        mbar_wait(kv_full, n_item & 1u);
-        for (int i = 0; i < NT; ++i, ++n_pair) {
+      uint32_t n_pair = 0, n_item = 0;   // n_item: items whose K/V have been waited for
+      int sl_cur = 0;
+      auto issue_scores = [&](const AbPair& pr, uint32_t np, int sl) {
+        const int st = int(np & 1u);
+        mbar_wait(qd_full(st), (np >> 1) & 1u);
+        tc_fence_after();
+        const uint64_t k_desc = make_smem_desc_sw128(smem_base + kAbSmemK + sl * kAbT);
+        const uint64_t v_desc = make_smem_desc_sw128(smem_base + kAbSmemV + sl * kAbT);
+        const uint64_t q_desc = make_smem_desc_sw128(smem_base + kAbSmemQ + st * kAbT);
+        const uint64_t do_desc = make_smem_desc_sw128(smem_base + kAbSmemDO + st * kAbT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // S^T = K Q^T
+          umma_f16_ss<1>(tmem_base + kAbTmS, k_desc + uint64_t(2 * k), q_desc + uint64_t(2 * k), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dP^T = V dO^T
+          umma_f16_ss<1>(tmem_base + kAbTmDP, v_desc + uint64_t(2 * k), do_desc + uint64_t(2 * k), id_s, k > 0);
+        umma_commit(s_full);
+        (void)pr;
+      };
+      AbPair cur = ab_first(p, NT);
+      if (cur.valid) {
+        mbar_wait(kv_full(0), 0u);
+        n_item = 1;
+        issue_scores(cur, 0u, 0);
+      }
+      while (cur.valid) {
+        const AbPair nxt = ab_next(cur, p, NT);
+        int sl_nxt = sl_cur;
+        if (nxt.valid) {
+          mbar_wait(s_empty, n_pair & 1u);          // pair n's scores are in registers: S / dP TMEM is free
+          if (nxt.i == 0) {                         // next pair opens a new (work item, key tile): its K / V slot
+            sl_nxt = int(n_item & 1u);
+            mbar_wait(kv_full(sl_nxt), (n_item >> 1) & 1u);
+            ++n_item;
+          }
+          issue_scores(nxt, n_pair + 1, sl_nxt);
+        }
+        mbar_wait(p_full, n_pair & 1u);             // P^T / dS^T of pair n are in smem; older dQ / dK / dV drains done
+        tc_fence_after();
+        {
           const int st = int(n_pair & 1u);
+          const uint64_t k_desc = make_smem_desc_sw128(smem_base + kAbSmemK + sl_cur * kAbT);
           const uint64_t q_desc = make_smem_desc_sw128(smem_base + kAbSmemQ + st * kAbT);
           const uint64_t do_desc = make_smem_desc_sw128(smem_base + kAbSmemDO + st * kAbT);
-          mbar_wait(qd_full(st), (n_pair >> 1) & 1u);
-          mbar_wait(s_empty, (n_pair & 1u) ^ 1u);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // S^T = K Q^T
-            umma_f16_ss<1>(tmem_base + kAbTmS, k_desc + uint64_t(2 * k), q_desc + uint64_t(2 * k), id_s, k > 0);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // dP^T = V dO^T
-            umma_f16_ss<1>(tmem_base + kAbTmDP, v_desc + uint64_t(2 * k), do_desc + uint64_t(2 * k), id_s, k > 0);
-          umma_commit(s_full);
-          mbar_wait(p_full, n_pair & 1u);
-          if (i == 0) mbar_wait(kvacc_empty, (n_item & 1u) ^ 1u);
-          mbar_wait(dq_empty, (n_pair & 1u) ^ 1u);
-          tc_fence_after();
+          const uint32_t acc_kv = cur.i > 0 ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {   // 16 queries per step: A chunk (k/4) 16 KB further, 32 B per step; B 2 KB per step
             const uint64_t a_off = uint64_t((k >> 2) * (kAbT >> 4) + 2 * (k & 3));
             const uint64_t b_off = uint64_t(k * (2048 >> 4));
-            umma_f16_ss<1>(tmem_base + kAbTmDV, p_desc + a_off, do_desc + b_off, id_kv, (i > 0 || k > 0) ? 1u : 0u);
-            umma_f16_ss<1>(tmem_base + kAbTmDK, ds_desc + a_off, q_desc + b_off, id_kv, (i > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ss<1>(tmem_base + kAbTmDV, p_desc + a_off, do_desc + b_off, id_kv, (acc_kv || k > 0) ? 1u : 0u);
+            umma_f16_ss<1>(tmem_base + kAbTmDK, ds_desc + a_off, q_desc + b_off, id_kv, (acc_kv || k > 0) ? 1u : 0u);
           }
+          // dQ_i: resident mode keeps one accumulator per query tile across the key tiles of this (batch, head)
+          const uint32_t dq_col = kAbTmDQ + (p.resident ? uint32_t(64 * cur.i) : 0u);
+          const uint32_t acc_q = (p.resident && cur.j > 0) ? 1u : 0u;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {   // dQ = dS K: 16 keys (= 16 smem rows = 2 KB) per step on both operands
             const uint64_t off = uint64_t(k * (2048 >> 4));
-            umma_f16_ss<1>(tmem_base + kAbTmDQ, ds_mn_desc + off, k_desc + off, id_dq, k > 0);
+            umma_f16_ss<1>(tmem_base + dq_col, ds_mn_desc + off, k_desc + off, id_dq, (acc_q || k > 0) ? 1u : 0u);
           }
           umma_commit(pv_done);
           umma_commit(qd_empty(st));
+          if (cur.i == NT - 1) umma_commit(kv_empty(sl_cur));
         }
-        umma_commit(kvacc_full);
-        umma_commit(kv_empty);
+        cur = nxt;
+        sl_cur = sl_nxt;
+        ++n_pair;
       }
     }
   } else {
@@ -225,17 +298,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const uint32_t row_smem = uint32_t(r * 128);
     const uint32_t swz = uint32_t(r & 7);
     float* stat = reinterpret_cast<float*>(smem_gen + kAbSmemStat);
-    uint32_t n_item = 0, n_pair = 0;
+    uint32_t n_pair = 0;
     const float c = p.scale_log2, sc = p.scale;
-    // lse2 / delta of a query tile are fetched one (key tile, query tile) pair ahead by warps 0-3 (one query row per
-    // thread), so their global-load latency hides behind the previous pair (padded queries: +inf / 0 -> P = 0)
+    // lse2 / delta of a query tile are fetched one pair ahead by warps 0-3 (one query row per thread), so their
+    // global-load latency hides behind the previous pair (padded queries: +inf / 0 -> P = 0)
     float pf_l = INFINITY, pf_d = 0.f;
-    auto prefetch_stats = [&](int bh_, int i_) {
+    auto prefetch_stats = [&](const AbPair& pr) {
       pf_l = INFINITY;
       pf_d = 0.f;
-      if (hf == 0 && bh_ < p.num_bh) {
-        const int h_ = bh_ % H, b_ = bh_ / H;
-        const int qi = i_ * 128 + r;
+      if (hf == 0 && pr.valid) {
+        const int bh_ = ab_bh(pr, p, NT), h_ = bh_ % H, b_ = bh_ / H;
+        const int qi = pr.i * 128 + r;
         if (qi < p.N) {
           const size_t off = (size_t(b_) * H + h_) * p.N + qi;
           pf_l = p.lse2[off];
@@ -243,145 +316,142 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         }
       }
     };
-    prefetch_stats(p.owner ? int(blockIdx.x) : int(blockIdx.x) / NT, 0);
-    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x)
-    for (int j = (p.owner ? 0 : w % NT), j1 = (p.owner ? NT : j + 1); j < j1; ++j, ++n_item) {
-      const int bh = p.owner ? w : w / NT;
-      const int h = bh % H, b = bh / H;
-      const bool key_ok = (j * 128 + r) < p.N;
-      for (int i = 0; i < NT; ++i, ++n_pair) {
-        float* st_l = stat + (n_pair & 1u) * 256;
-        if (hf == 0) {
-          st_l[r] = pf_l;
-          st_l[128 + r] = pf_d;
+    // dQ of one pair leaves TMEM (this warp: 32 query rows x 32 of the 64 columns)
+    auto drain_dq = [&](const AbPair& pr) {
+      const int bh_ = ab_bh(pr, p, NT), h_ = bh_ % H, b_ = bh_ / H;
+      const int qi = pr.i * 128 + r;
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDQ + (p.resident ? uint32_t(64 * pr.i) : 0u) + uint32_t(32 * hf), o);
+      tmem_wait_ld();
+      tc_fence_before();
+      if (qi >= p.N) return;
+      float* accp = p.dq_acc + ((size_t(b_) * p.N + qi) * H + h_) * 64 + 32 * hf;
+      if (!p.owner) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(accp + e), "f"(__uint_as_float(o[e])),
+                       "f"(__uint_as_float(o[e + 1])), "f"(__uint_as_float(o[e + 2])), "f"(__uint_as_float(o[e + 3]))
+                       : "memory");
+        return;
+      }
+      // owner mode: this thread owns these 32 values for every key tile of the (batch, head)
+      if (!p.resident && pr.j > 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4 a = reinterpret_cast<const float4*>(accp)[e];
+          o[4 * e + 0] = __float_as_uint(__uint_as_float(o[4 * e + 0]) + a.x);
+          o[4 * e + 1] = __float_as_uint(__uint_as_float(o[4 * e + 1]) + a.y);
+          o[4 * e + 2] = __float_as_uint(__uint_as_float(o[4 * e + 2]) + a.z);
+          o[4 * e + 3] = __float_as_uint(__uint_as_float(o[4 * e + 3]) + a.w);
         }
-        named_bar_sync(1, 32 * kAbComputeWarps);
-        if (i + 1 < NT) prefetch_stats(bh, i + 1);
-        else if (j + 1 < j1) prefetch_stats(bh, 0);
-        else prefetch_stats((w + int(gridDim.x)) < p.num_work ? (p.owner ? w + int(gridDim.x) : (w + int(gridDim.x)) / NT)
-                                                               : p.num_bh, 0);
-        mbar_wait(s_full, n_pair & 1u);
-        tc_fence_after();
+      }
+      if (pr.j + 1 < NT) {   // (never reached in resident mode: only the last key tile is drained)
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {   // two 32-query slices of this warp's 64-query half
-          uint32_t s[32], dp[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmS + uint32_t(64 * hf + 32 * sub), s);
-          tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDP + uint32_t(64 * hf + 32 * sub), dp);
-          tmem_wait_ld();
-          if (sub == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);
-          }
+        for (int e = 0; e < 8; ++e)
+          reinterpret_cast<float4*>(accp)[e] = make_float4(__uint_as_float(o[4 * e]), __uint_as_float(o[4 * e + 1]),
+                                                           __uint_as_float(o[4 * e + 2]), __uint_as_float(o[4 * e + 3]));
+      } else {
+        __nv_bfloat16* dst = p.dqkv + ((size_t(b_) * p.N + qi) * 3) * H * 64 + size_t(h_) * 64 + 32 * hf;   // q slot
+        st_global_bf16x16(dst, o);
+        st_global_bf16x16(dst + 16, o + 16);
+      }
+    };
+    // dK_j / dV_j of a finished key tile leave TMEM: warps 0-3 store dK (slot 1), warps 4-7 dV (slot 2)
+    auto drain_kv = [&](const AbPair& pr) {
+      const int bh_ = ab_bh(pr, p, NT), h_ = bh_ % H, b_ = bh_ / H;
+      const int kv = pr.j * 128 + r;
+      __nv_bfloat16* dst = p.dqkv + ((size_t(b_) * p.N + kv) * 3 + size_t(hf + 1)) * H * 64 + size_t(h_) * 64;
+      const uint32_t tcol = hf == 0 ? kAbTmDK : kAbTmDV;
+      uint32_t o[64];
+      tmem_ld_32x32b_x32_at<0>(tmem_base + lane_off + tcol, o);
+      tmem_ld_32x32b_x32_at<32>(tmem_base + lane_off + tcol + 32u, o);
+      tmem_wait_ld();
+      tc_fence_before();
+      if (kv < p.N) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {   // four 16-byte groups = 8 queries each
-            uint32_t pp[4], dd[4];
+        for (int e = 0; e < 64; e += 16) st_global_bf16x16(dst + e, o + e);
+      }
+    };
+    auto needs_drain = [&](const AbPair& pr) { return !p.resident || pr.j == NT - 1; };
+
+    AbPair cur = ab_first(p, NT);
+    prefetch_stats(cur);
+    // Results of pair n (its dQ; dK_j / dV_j when it closes a key tile) stay in TMEM until the middle of pair n+1: by
+    // then their MMAs have retired (no idle wait), and the MMAs that overwrite those accumulators are only issued
+    // after pair n+1's p_full, which this warp signals after the drain.
+    AbPair pending = cur;
+    bool pend_dq = false, pend_kv = false;
+    for (; cur.valid; ++n_pair) {
+      const AbPair nxt = ab_next(cur, p, NT);
+      const bool key_ok = (cur.j * 128 + r) < p.N;
+      float* st_l = stat + (n_pair & 1u) * 256;
+      if (hf == 0) {
+        st_l[r] = pf_l;
+        st_l[128 + r] = pf_d;
+      }
+      named_bar_sync(1, 32 * kAbComputeWarps);
+      prefetch_stats(nxt);
+      mbar_wait(s_full, n_pair & 1u);
+      tc_fence_after();
+      uint32_t pp[2][16], dd[2][16];     // bf16x2-packed P^T / dS^T of the two 32-query slices of this warp's half
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c0 = 8 * g + 2 * e;
-              const float2 l2 = *reinterpret_cast<const float2*>(st_l + 64 * hf + 32 * sub + c0);
-              const float2 dl = *reinterpret_cast<const float2*>(st_l + 128 + 64 * hf + 32 * sub + c0);
-              float p0 = ex2f(fmaf(__uint_as_float(s[c0]), c, -l2.x));
-              float p1 = ex2f(fmaf(__uint_as_float(s[c0 + 1]), c, -l2.y));
-              if (!key_ok) { p0 = 0.f; p1 = 0.f; }
-              const float d0 = p0 * (__uint_as_float(dp[c0]) - dl.x) * sc;
-              const float d1 = p1 * (__uint_as_float(dp[c0 + 1]) - dl.y) * sc;
-              pp[e] = pack_bf16x2(p0, p1);
-              dd[e] = pack_bf16x2(d0, d1);
-            }
-            const uint32_t a = row_smem + uint32_t(hf * kAbT) + ((uint32_t(4 * sub + g) ^ swz) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemP + a), "r"(pp[0]),
-                         "r"(pp[1]), "r"(pp[2]), "r"(pp[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemDS + a), "r"(dd[0]),
-                         "r"(dd[1]), "r"(dd[2]), "r"(dd[3]) : "memory");
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        // ---- dQ partial of this (key tile, query tile) pair (32 of the 64 columns per warp) ----
-        const int qi = i * 128 + r;
-        float* accp = p.dq_acc + ((size_t(b) * p.N + qi) * H + h) * 64 + 32 * hf;
-        float4 prev[8];
-        const bool rmw = p.owner && j > 0 && qi < p.N;
-        if (rmw) {   // owner mode: the partial of the previous key tiles, fetched while the MMAs of this pair run
-#pragma unroll
-          for (int e = 0; e < 8; ++e) prev[e] = reinterpret_cast<const float4*>(accp)[e];
-        }
-        mbar_wait(pv_done, n_pair & 1u);   // also: P^T / dS^T smem may be overwritten from here on
-        tc_fence_after();
-        {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDQ + uint32_t(32 * hf), o);
-          tmem_wait_ld();
+      for (int sub = 0; sub < 2; ++sub) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmS + uint32_t(64 * hf + 32 * sub), s);
+        tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDP + uint32_t(64 * hf + 32 * sub), dp);
+        tmem_wait_ld();
+        if (sub == 1) {
+          // both slices are in registers: the tensor core may start the next pair's scores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(dq_empty);
-          if (qi < p.N) {
-            if (!p.owner) {
+          if (lane == 0) mbar_arrive(s_empty);
+        }
 #pragma unroll
-              for (int e = 0; e < 32; e += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(accp + e),
-                             "f"(__uint_as_float(o[e])), "f"(__uint_as_float(o[e + 1])),
-                             "f"(__uint_as_float(o[e + 2])), "f"(__uint_as_float(o[e + 3])) : "memory");
-            } else {
-              // the same thread owns these 32 values for every key tile of this (batch, head): plain read-modify-write
-              if (rmw) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  o[4 * e + 0] = __float_as_uint(__uint_as_float(o[4 * e + 0]) + prev[e].x);
-                  o[4 * e + 1] = __float_as_uint(__uint_as_float(o[4 * e + 1]) + prev[e].y);
-                  o[4 * e + 2] = __float_as_uint(__uint_as_float(o[4 * e + 2]) + prev[e].z);
-                  o[4 * e + 3] = __float_as_uint(__uint_as_float(o[4 * e + 3]) + prev[e].w);
-                }
-              }
-              if (j + 1 < NT) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  reinterpret_cast<float4*>(accp)[e] = make_float4(__uint_as_float(o[4 * e]), __uint_as_float(o[4 * e + 1]),
-                                                                   __uint_as_float(o[4 * e + 2]), __uint_as_float(o[4 * e + 3]));
-              } else {
-                __nv_bfloat16* dst = p.dqkv + ((size_t(b) * p.N + qi) * 3) * H * 64 + size_t(h) * 64 + 32 * hf;   // q slot
-#pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                  uint4 wv;
-                  wv.x = pack_bf16x2(__uint_as_float(o[e]), __uint_as_float(o[e + 1]));
-                  wv.y = pack_bf16x2(__uint_as_float(o[e + 2]), __uint_as_float(o[e + 3]));
-                  wv.z = pack_bf16x2(__uint_as_float(o[e + 4]), __uint_as_float(o[e + 5]));
-                  wv.w = pack_bf16x2(__uint_as_float(o[e + 6]), __uint_as_float(o[e + 7]));
-                  *reinterpret_cast<uint4*>(dst + e) = wv;
-                }
-              }
-            }
-          }
+        for (int e = 0; e < 16; ++e) {
+          const int c0 = 2 * e;
+          const float2 l2 = *reinterpret_cast<const float2*>(st_l + 64 * hf + 32 * sub + c0);
+          const float2 dl = *reinterpret_cast<const float2*>(st_l + 128 + 64 * hf + 32 * sub + c0);
+          float p0 = ex2f(fmaf(__uint_as_float(s[c0]), c, -l2.x));
+          float p1 = ex2f(fmaf(__uint_as_float(s[c0 + 1]), c, -l2.y));
+          if (!key_ok) { p0 = 0.f; p1 = 0.f; }
+          const float d0 = p0 * (__uint_as_float(dp[c0]) - dl.x) * sc;
+          const float d1 = p1 * (__uint_as_float(dp[c0 + 1]) - dl.y) * sc;
+          pp[sub][e] = pack_bf16x2(p0, p1);
+          dd[sub][e] = pack_bf16x2(d0, d1);
         }
       }
-      // ---- dK_j, dV_j leave TMEM once per item: warps 0-3 store dK (slot 1), warps 4-7 dV (slot 2) ----
-      mbar_wait(kvacc_full, n_item & 1u);
+      // P^T / dS^T smem still feeds the previous pair's dV / dK / dQ MMAs: wait for them, and take its results out
+      if (n_pair > 0) {
+        mbar_wait(pv_done, (n_pair - 1) & 1u);
+        tc_fence_after();
+        if (pend_dq) drain_dq(pending);
+        if (pend_kv) drain_kv(pending);
+      }
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {   // four 16-byte groups = 8 queries each
+          const uint32_t a = row_smem + uint32_t(hf * kAbT) + ((uint32_t(4 * sub + g) ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemP + a), "r"(pp[sub][4 * g]),
+                       "r"(pp[sub][4 * g + 1]), "r"(pp[sub][4 * g + 2]), "r"(pp[sub][4 * g + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_base + kAbSmemDS + a), "r"(dd[sub][4 * g]),
+                       "r"(dd[sub][4 * g + 1]), "r"(dd[sub][4 * g + 2]), "r"(dd[sub][4 * g + 3]) : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      pending = cur;
+      pend_dq = needs_drain(cur);
+      pend_kv = (cur.i == NT - 1);
+      cur = nxt;
+    }
+    if (n_pair > 0) {   // results of the last pair
+      mbar_wait(pv_done, (n_pair - 1) & 1u);
       tc_fence_after();
-      {
-        const int kv = j * 128 + r;
-        __nv_bfloat16* dst = p.dqkv + ((size_t(b) * p.N + kv) * 3 + size_t(hf + 1)) * H * 64 + size_t(h) * 64;
-        const uint32_t tcol = hf == 0 ? kAbTmDK : kAbTmDV;
-        uint32_t o[64];
-        tmem_ld_32x32b_x32_at<0>(tmem_base + lane_off + tcol, o);
-        tmem_ld_32x32b_x32_at<32>(tmem_base + lane_off + tcol + 32u, o);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(kvacc_empty);
-        if (key_ok) {
-#pragma unroll
-          for (int e = 0; e < 64; e += 8) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[e]), __uint_as_float(o[e + 1]));
-            w.y = pack_bf16x2(__uint_as_float(o[e + 2]), __uint_as_float(o[e + 3]));
-            w.z = pack_bf16x2(__uint_as_float(o[e + 4]), __uint_as_float(o[e + 5]));
-            w.w = pack_bf16x2(__uint_as_float(o[e + 6]), __uint_as_float(o[e + 7]));
-            *reinterpret_cast<uint4*>(dst + e) = w;
-          }
-        }
-      }
+      if (pend_dq) drain_dq(pending);
+      if (pend_kv) drain_kv(pending);
     }
   }
   __syncwarp();
@@ -409,6 +479,7 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
   MT_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) |
                reinterpret_cast<uintptr_t>(dqkv) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0,
              MT_ERR_BAD_ALIGN, "mt_attention_bwd: pointers must be 16-byte aligned");
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(dqkv) & 31) == 0, MT_ERR_BAD_ALIGN, "mt_attention_bwd: dqkv must be 32-byte aligned");
   const size_t dq_bytes = size_t(B) * N * H * 64 * 4;
   const size_t need = dq_bytes + size_t(B) * H * N * 4 + 256;
   MT_REQUIRE(workspace_bytes >= need, MT_ERR_BAD_SHAPE, "mt_attention_bwd: workspace too small (%zu < %zu)",
@@ -455,6 +526,8 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
     }
     p.owner = forced >= 0 ? forced : (p.num_bh >= 8 * sms || p.num_t == 1) ? 1 : 0;
   }
+  p.resident = (p.owner && p.num_t <= 2) ? 1 : 0;
+
   p.num_work = p.owner ? p.num_bh : p.num_bh * p.num_t;
   if (!p.owner) MT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   p.scale = scale;
