@@ -114,6 +114,17 @@ def test_transpose_and_colsum(mt):
     assert (cs.cpu() - x.sum(0)).abs().max() < 1e-3
 
 
+@pytest.mark.parametrize("M,N", [(50176, 3072), (50176, 768), (1000, 2304), (37, 8), (5, 264), (4096, 100), (3, 250000)])
+def test_colsum_bias_gradient(mt, M, N):
+    """db = column sums of dY in fp32 (vectorised kernel for N % 8 == 0, scalar kernel otherwise)"""
+    g = torch.Generator().manual_seed(M + N)
+    x = _bf16_round(torch.randn(M, N, generator=g))
+    cs = mt.ops.colsum(x.cuda().bfloat16())
+    ref = x.double().sum(0)
+    assert cs.dtype == torch.float32 and cs.shape == (N,)
+    assert (cs.double().cpu() - ref).abs().max() <= 1e-5 * M ** 0.5 * 8 + 1e-4
+
+
 def test_trainable_tokenizer_under_frozen_encoder(mt):
     """The AST training pattern (Audio/src/models/ast_models.py:66-70): encoder frozen, patch-embed conv trainable.
     Gradients of the conv weight / bias through 2 frozen Blocks vs fp64 autograd of the oracle."""

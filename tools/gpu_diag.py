@@ -204,6 +204,44 @@ def group_perf():
     print(f"[perf] layernorm M={M} d=768: {ms:.4f} ms  {M * 768 * 4 / ms / 1e6:.1f} GB/s", flush=True)
 
 
+def group_wgrad():
+    """fine-tune backward pieces at C2 size: the four weight-gradient GEMMs, bias column sums, recomputations"""
+    import torch
+    from metatransformer_b200 import ops
+    dev = torch.device("cuda")
+    M = 50176
+
+    def timeit(fn, iters=10):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for name, n, k in [("qkv", 2304, 768), ("proj", 768, 768), ("fc1", 3072, 768), ("fc2", 768, 3072)]:
+        dy = torch.randn(M, n, device=dev).bfloat16()
+        x = torch.randn(M, k, device=dev).bfloat16()
+        ms = timeit(lambda: ops.linear_wgrad(dy, x))
+        print(f"[wgrad] dW {name} [{n}x{k}] over {M} tokens: {ms:.4f} ms  {2.0 * M * n * k / ms / 1e9:.1f} TFLOP/s", flush=True)
+        ms = timeit(lambda: ops.colsum(dy))
+        print(f"[wgrad] colsum [{M}x{n}]: {ms:.4f} ms  {M * n * 2 / ms / 1e6:.1f} GB/s", flush=True)
+    u = torch.randn(M, 3072, device=dev).bfloat16()
+    ms = timeit(lambda: ops.gelu(u))
+    print(f"[wgrad] gelu [{M}x3072]: {ms:.4f} ms  {M * 3072 * 4 / ms / 1e6:.1f} GB/s", flush=True)
+    w = torch.randn(3072, 768, device=dev)
+    dwf = torch.randn(3072, 768, device=dev)
+    g = torch.ones(768, device=dev)
+    b = torch.zeros(768, device=dev)
+    dyb = torch.randn(3072, device=dev)
+    ms = timeit(lambda: ops.ln_fold_bwd(dwf, w, g, b, dyb))
+    print(f"[wgrad] ln_fold_bwd [3072x768]: {ms:.4f} ms", flush=True)
+
+
 def group_abw():
     """attention backward only: the four BASELINE shapes, 30 timed iterations each (MT_B200_ATTN_BWD_OWNER=0|1 for A/B)."""
     import torch
@@ -299,7 +337,7 @@ def group_prof_layer():
     torch.cuda.synchronize()
 
 
-GROUPS = {"abw": group_abw, "prof": group_prof, "prof_layer": group_prof_layer, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+GROUPS = {"wgrad": group_wgrad, "abw": group_abw, "prof": group_prof, "prof_layer": group_prof_layer, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
 
 
 def main():
