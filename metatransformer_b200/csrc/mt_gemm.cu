@@ -53,6 +53,7 @@ struct GemmParams {
   const float* bias;            // [N] fp32 or nullptr
   const __nv_bfloat16* resid;   // [M, ldr] bf16 (or [resid_period, ldr], see below) or nullptr
   int ldr;
+  int resid_ld256;              // residual rows are 32-byte aligned: fetch them with 256-bit loads
   int resid_period;             // > 0: output row m reads residual row m % resid_period (a [n, d] positional table
                                 // broadcast over the batch: tokenizer GEMMs)
   int M, N, K;
@@ -324,9 +325,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       auto load_resid = [&](int sc_, uint4 (&dst)[4]) {
         const int c_ = col0 + 32 * sc_;
         if (row_ok && c_ < p.N) {
-          const uint4* rp = reinterpret_cast<const uint4*>(rrow + c_);
+          if (p.resid_ld256) {
+            // two 32-byte loads: whole sectors per thread (rows are scattered, 16-byte loads would touch each sector twice)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = __ldg(rp + j);
+            for (int j = 0; j < 2; ++j)
+              asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                           : "=r"(dst[2 * j].x), "=r"(dst[2 * j].y), "=r"(dst[2 * j].z), "=r"(dst[2 * j].w),
+                             "=r"(dst[2 * j + 1].x), "=r"(dst[2 * j + 1].y), "=r"(dst[2 * j + 1].z), "=r"(dst[2 * j + 1].w)
+                           : "l"(rrow + c_ + 16 * j));
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(rrow + c_);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = __ldg(rp + j);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
@@ -503,6 +514,14 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   p.resid = reinterpret_cast<const __nv_bfloat16*>(resid);
   p.ldr = ldr;
   p.resid_period = resid_period;
+  {
+    static int ld256 = -1;   // MT_B200_RESID256=0 falls back to 16-byte loads (A/B runs)
+    if (ld256 < 0) {
+      const char* e = getenv("MT_B200_RESID256");
+      ld256 = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.resid_ld256 = (ld256 && resid != nullptr && (reinterpret_cast<uintptr_t>(resid) & 31) == 0 && (ldr % 16) == 0) ? 1 : 0;
+  }
   p.mn_major = mn_major;
   p.M = M; p.N = N; p.K = K;
   p.act = act;
