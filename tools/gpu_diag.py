@@ -204,6 +204,28 @@ def group_perf():
     print(f"[perf] layernorm M={M} d=768: {ms:.4f} ms  {M * 768 * 4 / ms / 1e6:.1f} GB/s", flush=True)
 
 
+def group_afw():
+    """attention forward only, C2 shape, 50 timed iterations (ablation runs via MT_B200_AFW_SKIP)"""
+    import torch
+    from metatransformer_b200 import ops
+    dev = torch.device("cuda")
+    for (B, N, H) in [(256, 196, 12), (32, 1568, 16)]:
+        qkv = torch.randn(B, N, 3 * H * 64, device=dev).bfloat16()
+        out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.attention(qkv, H, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            ops.attention(qkv, H, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 50
+        print(f"[afw skip={os.environ.get('MT_B200_AFW_SKIP', '0')}] B={B} N={N} H={H}: {ms:.4f} ms  "
+              f"{4.0 * B * H * N * N * 64 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def group_wgrad():
     """fine-tune backward pieces at C2 size: the four weight-gradient GEMMs, bias column sums, recomputations"""
     import torch
@@ -337,7 +359,7 @@ def group_prof_layer():
     torch.cuda.synchronize()
 
 
-GROUPS = {"wgrad": group_wgrad, "abw": group_abw, "prof": group_prof, "prof_layer": group_prof_layer, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
+GROUPS = {"afw": group_afw, "wgrad": group_wgrad, "abw": group_abw, "prof": group_prof, "prof_layer": group_prof_layer, "prof_fc1": group_prof_fc1, "prof_fc2": group_prof_fc2, "basic": group_basic, "gemm1": group_gemm1, "gemm2": group_gemm2, "attn": group_attn, "perf": group_perf}
 
 
 def main():
