@@ -12,13 +12,13 @@
 //     dV_j += P^T  dO_i           A = P^T  (smem, K-major),  B = dO_i (MN-major)     (TMEM cols 256..319)
 //     dK_j += dS^T Q_i            A = dS^T (smem, K-major),  B = Q_i  (MN-major)     (TMEM cols 320..383)
 //     dQ_i  = dS   K_j            A = dS^T read MN-major,     B = K_j  (MN-major)     (TMEM cols 384..447)
-//   Two work decompositions (picked on the host by the number of (batch, head) pairs per SM):
-//    * owner: a CTA owns one (batch, head) at a time and walks its key tiles j, so the dQ_i partials of successive key
-//      tiles are combined by the same thread with plain fp32 loads / stores on an L2-resident scratch (first tile
-//      stores, middle tiles add, the last tile adds and writes bf16 into the q slot; the loads are issued before the
-//      wait on the MMAs) — no atomics, no zero-fill, no conversion pass, deterministic;
-//    * split: work item = (batch, head, key tile) for few, long sequences; dQ_i partials are added to a zero-filled
-//      fp32 accumulator with red.global.add and converted to bf16 by a small kernel afterwards.
+//   Work decomposition (picked on the host by the number of (batch, head) pairs per SM):
+//    * owner: a CTA owns one (batch, head) at a time and walks its key tiles j; with <= 2 key tiles (N <= 256) dQ_i
+//      stays RESIDENT in TMEM across the key tiles (one accumulator per query tile, accumulate flag of tcgen05.mma)
+//      and is written once, as bf16 — no atomics, no scratch, no zero-fill, no conversion pass, deterministic;
+//    * split: work item = (batch, head, key tile) for few, long sequences.
+//   Whenever dQ is not resident, each warp stages its 32 x 32 fp32 partial in shared memory and the TMA engine adds
+//   it to a zero-filled fp32 accumulator (cp.reduce.async.bulk.tensor ... add); a small kernel converts to bf16.
 //   dK_j / dV_j leave once per key tile.
 //   lse2 = log2-sum-exp saved by the forward, delta_i = rowsum(dO_i * O_i) from a small pre-pass kernel.
 // Warps: 0-7 compute (warp & 3 = TMEM lane quarter = 32 key rows, warp >> 2 = which 64-query half of the tile),
@@ -36,12 +36,16 @@ constexpr int kAbSmemQ = kAbSmemV + 2 * kAbT;   // 2 stages
 constexpr int kAbSmemDO = kAbSmemQ + 2 * kAbT;
 constexpr int kAbSmemP = kAbSmemDO + 2 * kAbT;   // P^T: 2 chunks of 64 queries
 constexpr int kAbSmemDS = kAbSmemP + 2 * kAbT;   // dS^T
-constexpr int kAbSmemStat = kAbSmemDS + 2 * kAbT;  // 2 x (128 lse2 + 128 delta) floats
+constexpr int kAbSmemStage = kAbSmemDS + 2 * kAbT;   // dQ partial staging: 8 warps x (32 rows x 32 fp32), 128B-swizzled
+constexpr int kAbSmemStat = kAbSmemStage + 8 * 4096;  // 2 x (128 lse2 + 128 delta) floats
 constexpr int kAbSmemBar = kAbSmemStat + 2 * 256 * 4;
 // barriers: kv_full[2] kv_empty[2] qd_full[2] qd_empty[2] s_full s_empty p_full pv_done
 constexpr int kAbNumBars = 12;
 constexpr int kAbSmemTmemPtr = kAbSmemBar + kAbNumBars * 8;
-constexpr int kAbSmemBytes = kAbSmemTmemPtr + 16 + 1024;
+// No alignment slack: the dynamic shared memory window of a kernel without static __shared__ data starts 1 KB-aligned
+// (checked at kernel entry), and 6 x 32 KB of tiles + 32 KB of staging leave < 1 KB of the 227 KB.
+constexpr int kAbSmemBytes = kAbSmemTmemPtr + 16;
+static_assert(kAbSmemBytes <= 227 * 1024, "attention_bwd_kernel: shared memory budget");
 constexpr int kAbThreads = 320;
 constexpr int kAbComputeWarps = 8;
 constexpr uint32_t kAbTmS = 0, kAbTmDP = 128, kAbTmDV = 256, kAbTmDK = 320, kAbTmDQ = 384;   // dQ: 384 (+64 resident #2)
@@ -56,7 +60,7 @@ struct AttnBwdParams {
   float scale, scale_log2;
   const float* lse2;     // [B, H, N]
   const float* delta;    // [B, H, N]
-  float* dq_acc;         // [B, N, H, 64] fp32: scratch (owner, num_t > 2) or zero-filled accumulator (split)
+  float* dq_acc;         // [B, N, H, 64] fp32 zero-filled accumulator (unused in resident mode)
   __nv_bfloat16* dqkv;   // [B, N, 3, H, 64]
 };
 
@@ -153,10 +157,14 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_store_kernel(const float* __r
 
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                     const AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+                     const __grid_constant__ CUtensorMap tm_dq, const AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  uint8_t* smem_gen = smem_raw;
+  if ((smem_base & 1023u) != 0u) {   // the 128B-swizzled tiles need 1 KB alignment
+    if (threadIdx.x == 0) printf("[mt_b200] attention_bwd_kernel: dynamic smem base 0x%x is not 1 KB aligned\n", smem_base);
+    __trap();
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_base + kAbSmemBar;
   auto kv_full = [&](int s) { return bar0 + 8u * s; };
@@ -169,6 +177,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
     for (int s = 0; s < 2; ++s) {
       mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1);
       mbar_init(qd_full(s), 1); mbar_init(qd_empty(s), 1);
@@ -317,6 +326,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
     };
     // dQ of one pair leaves TMEM (this warp: 32 query rows x 32 of the 64 columns)
+    bool stage_pending = false;   // this warp's staging buffer is being read by an earlier TMA reduce
     auto drain_dq = [&](const AbPair& pr) {
       const int bh_ = ab_bh(pr, p, NT), h_ = bh_ % H, b_ = bh_ / H;
       const int qi = pr.i * 128 + r;
@@ -324,33 +334,32 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       tmem_ld_32x32b_x32(tmem_base + lane_off + kAbTmDQ + (p.resident ? uint32_t(64 * pr.i) : 0u) + uint32_t(32 * hf), o);
       tmem_wait_ld();
       tc_fence_before();
-      if (qi >= p.N) return;
-      float* accp = p.dq_acc + ((size_t(b_) * p.N + qi) * H + h_) * 64 + 32 * hf;
-      if (!p.owner) {
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(accp + e), "f"(__uint_as_float(o[e])),
-                       "f"(__uint_as_float(o[e + 1])), "f"(__uint_as_float(o[e + 2])), "f"(__uint_as_float(o[e + 3]))
-                       : "memory");
-        return;
-      }
-      // owner mode: this thread owns these 32 values for every key tile of the (batch, head)
-      if (!p.resident && pr.j > 0) {
+      if (!p.resident) {
+        // partial of one key tile: staged in this warp's 4 KB of shared memory (128B swizzle) and added to the fp32
+        // accumulator in HBM by the TMA engine (one bulk reduce per warp instead of 8 scattered 16-byte atomics per
+        // thread; rows beyond N are clipped by the tensor map)
+        const uint32_t stg = smem_base + kAbSmemStage + uint32_t(warp) * 4096u;
+        if (stage_pending) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float4 a = reinterpret_cast<const float4*>(accp)[e];
-          o[4 * e + 0] = __float_as_uint(__uint_as_float(o[4 * e + 0]) + a.x);
-          o[4 * e + 1] = __float_as_uint(__uint_as_float(o[4 * e + 1]) + a.y);
-          o[4 * e + 2] = __float_as_uint(__uint_as_float(o[4 * e + 2]) + a.z);
-          o[4 * e + 3] = __float_as_uint(__uint_as_float(o[4 * e + 3]) + a.w);
+          const uint32_t addr = stg + uint32_t(lane * 128) + ((uint32_t(e) ^ uint32_t(lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[4 * e]), "r"(o[4 * e + 1]),
+                       "r"(o[4 * e + 2]), "r"(o[4 * e + 3]) : "memory");
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_4d(&tm_dq, stg, 32 * hf, h_, pr.i * 128 + 32 * q4, b_);
+          tma_store_commit();
+        }
+        stage_pending = true;
+        return;
       }
-      if (pr.j + 1 < NT) {   // (never reached in resident mode: only the last key tile is drained)
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          reinterpret_cast<float4*>(accp)[e] = make_float4(__uint_as_float(o[4 * e]), __uint_as_float(o[4 * e + 1]),
-                                                           __uint_as_float(o[4 * e + 2]), __uint_as_float(o[4 * e + 3]));
-      } else {
+      if (qi >= p.N) return;
+      {
         __nv_bfloat16* dst = p.dqkv + ((size_t(b_) * p.N + qi) * 3) * H * 64 + size_t(h_) * 64 + 32 * hf;   // q slot
         st_global_bf16x16(dst, o);
         st_global_bf16x16(dst + 16, o + 16);
@@ -453,6 +462,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       if (pend_dq) drain_dq(pending);
       if (pend_kv) drain_kv(pending);
     }
+    if (stage_pending) {
+      if (lane == 0) tma_store_wait_all<0>();
+      __syncwarp();
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -529,7 +542,7 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
   p.resident = (p.owner && p.num_t <= 2) ? 1 : 0;
 
   p.num_work = p.owner ? p.num_bh : p.num_bh * p.num_t;
-  if (!p.owner) MT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
+  if (!p.resident) MT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, dq_bytes, s));
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse2 = lse2;
@@ -547,9 +560,18 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
-  attention_bwd_kernel<<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, p);
+  CUtensorMap tm_dq;
+  {
+    // fp32 dQ accumulator [B, N, H, 64]: one warp's partial = 32 query rows x 32 of the 64 columns (128 B rows)
+    uint64_t dims[4] = {64, uint64_t(H), uint64_t(N), uint64_t(B)};
+    uint64_t strides[3] = {64 * 4, uint64_t(H) * 64 * 4, uint64_t(N) * H * 64 * 4};
+    uint32_t box[4] = {32, 1, 32, 1};
+    int rc2 = encode_tmap(&tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc2) return rc2;
+  }
+  attention_bwd_kernel<<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, tm_dq, p);
   MT_CHECK_CUDA(cudaGetLastError());
-  if (!p.owner) {
+  if (!p.resident) {
     const long long rows = (long long)B * N;
     long long blocks = (rows * H * 8 + 255) / 256;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;

@@ -138,6 +138,12 @@ MT_DEVINL void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int 
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// element-wise += of a shared-memory tile into global memory by the TMA engine (fp32 add; out-of-range rows are clipped)
+MT_DEVINL void tma_reduce_add_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 MT_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 MT_DEVINL void tma_store_wait_read() {
