@@ -162,7 +162,7 @@ def run_ours(args):
     import metatransformer_b200 as mt
     from metatransformer_b200 import ops
     from metatransformer_b200.distributed import init_process_group
-    from oracle import encoder_oracle as orc   # checker + cpu_baseline leg only
+    from metatransformer_b200 import synthetic
 
     rank, local_rank, world = init_process_group("nccl")
     if world != args.gpus and world > 1:
@@ -172,7 +172,7 @@ def run_ours(args):
     sustained_tf, burst_tf, hbm_gbs, peak_src = _peaks()
 
     # ---- model: identical seeded weights on every rank, inputs seeded per rank ----
-    sd = orc.make_encoder_state_dict(D, DEPTH, seed=0)
+    sd = synthetic.make_encoder_state_dict(D, DEPTH, seed=0)
     enc = mt.build_encoder("base")
     enc.load_state_dict(sd, strict=True)
     enc = enc.to(dev).eval()
@@ -188,7 +188,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- parity spot check against the oracle (first 2 sequences) ----
+    # ---- parity spot check (first 2 sequences): the oracle is used here as the checker only ----
+    from oracle import encoder_oracle as orc
     with torch.no_grad():
         got = fused(xs[0][:2].contiguous()).float().cpu()
     w16 = {k: (v.bfloat16().float() if v.dim() == 2 else v) for k, v in sd.items()}
@@ -218,7 +219,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * tokens_per_step * args.steps / (ms_total * 1e-3)
-    flops_step = orc.encoder_flops(B, N, D, DEPTH)
+    flops_step = synthetic.encoder_flops(B, N, D, DEPTH)
 
     # ---- end to end through the public API with pinned host buffers (3-slot software pipeline) ----
     SLOTS = 3

@@ -126,3 +126,14 @@ def test_block_dropout_configuration_is_accepted_and_attn_drop_documented():
     assert blk.attn.proj_drop.p == 0.1 and blk.mlp.drop.p == 0.1 and blk.drop_path.drop_prob == 0.2
     assert blk._is_stochastic() and not blk.eval()._is_stochastic()
     assert mt.Block(64, 2)._is_stochastic() is False
+
+
+def test_package_synthetic_generators_match_the_oracle_copy():
+    """bench.py / tools seed their weights from metatransformer_b200.synthetic (nothing measured imports oracle/); the
+    oracle's own generators must stay bit-identical so that parity checks compare like with like."""
+    from metatransformer_b200 import synthetic
+    from oracle import encoder_oracle as orc
+    a, b = synthetic.make_encoder_state_dict(64, 2, seed=3), orc.make_encoder_state_dict(64, 2, seed=3)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(synthetic.make_tokens(2, 5, 64, seed=7), orc.make_tokens(2, 5, 64, seed=7))
+    assert synthetic.encoder_flops(256, 196, 768, 12) == orc.encoder_flops(256, 196, 768, 12) == 256 * 196 * 177094656.0

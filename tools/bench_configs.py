@@ -11,7 +11,7 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import metatransformer_b200 as mt  # noqa: E402
-from oracle import encoder_oracle as orc  # noqa: E402  (FLOP formula + seeded weights only)
+from metatransformer_b200 import synthetic as orc  # noqa: E402  (seeded weights + FLOP formula)
 
 CFG = {
     "C2": dict(scale="base", B=256, N=196, tok=None),

@@ -347,7 +347,7 @@ def group_prof_layer():
     """one Base-16 layer's worth of kernels at C2 size through the fused driver (for ncu --set full captures)"""
     import torch
     import metatransformer_b200 as mt
-    from oracle import encoder_oracle as orc
+    from metatransformer_b200 import synthetic as orc
     enc = mt.build_encoder("base", depth=2)
     enc.load_state_dict(orc.make_encoder_state_dict(768, 2, seed=0), strict=True)
     enc = enc.cuda().eval()
