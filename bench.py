@@ -197,6 +197,13 @@ def run_ours(args):
     parity = {"max_abs_err": float((got - ref).abs().max()), "rel_l2_err": float((got - ref).norm() / ref.norm()),
               "ref_abs_max": float(ref.abs().max()), "checked": "first 2 sequences vs fp32 CPU oracle"}
 
+    # ---- set-up outside any timing: one call per rotating input buffer so that every CUDA graph FusedEncoder keeps
+    #      (keyed on the input / output pointers) is captured before the warm-up steps start, whatever W is ----
+    with torch.no_grad():
+        for i in range(NBUF):
+            fused(xs[i], out=y)
+    torch.cuda.synchronize()
+
     # ---- device-resident throughput ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -250,6 +257,7 @@ def run_ours(args):
         s_d2h.synchronize()
 
     with torch.no_grad():
+        e2e_steps(SLOTS)                      # set-up: one pass per slot captures the slot's CUDA graph
         e2e_steps(min(args.warmup, 3))
         barrier()
         t0 = time.perf_counter()
