@@ -91,7 +91,6 @@ MT_DEVINL int pooled_rows(const __nv_bfloat16* __restrict__ xb, int N, int d, in
     return nr;
   }
   // mean over tokens: thread = (column vector cv, row group rg); partial sums per row group in `scratch`
-  const int groups = max(1, min(kPoolThreads / d8, 8));
   for (int cv0 = 0; cv0 < d8; cv0 += kPoolThreads) {   // d8 > 256 (d > 2048): several column passes
     const int span = min(d8 - cv0, kPoolThreads);
     const int g = (span < kPoolThreads) ? max(1, min(kPoolThreads / span, 8)) : 1;
@@ -115,7 +114,6 @@ MT_DEVINL int pooled_rows(const __nv_bfloat16* __restrict__ xb, int N, int d, in
     }
     __syncthreads();
   }
-  (void)groups;
   return 1;
 }
 
