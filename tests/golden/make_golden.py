@@ -11,6 +11,12 @@ What is executed from the reference tree (never copied into this repo):
     and exec the two source files unmodified.
   * Data2Seq/Image.py       -> PatchEmbed (imports only torch)
   * Data2Seq/Time_Series.py -> DataEmbedding (imports only torch)
+  * Audio/src/models/ast_models.py        -> class PatchEmbed (:18-33) with its `proj` replaced exactly as ASTModel does
+    (:86: Conv2d(1, d, (16,16), stride=(fstride, tstride)))
+  * Video/models/modeling_finetune.py     -> class PatchEmbed (:263-297), the tubelet Conv3d tokenizer
+    Both files `import timm` / `wget` at the top; those modules are absent here, so tiny stand-ins providing only
+    `to_2tuple`, `trunc_normal_`, `drop_path`, `register_model` are placed in sys.modules and the files are exec'd
+    unmodified (only the two PatchEmbed classes are used).
 The vectors land in tests/golden/*.npz (small, committed).  /root/reference does not exist on the GPU box, so tests
 only ever read the .npz files.
 """
@@ -75,6 +81,23 @@ def _load_file_module(name, path):
     return mod
 
 
+def _stub_timm():
+    """Stand-ins for the names the two model files import from timm / wget at module level."""
+    if "timm" in sys.modules:
+        return
+    timm = types.ModuleType("timm")
+    models = types.ModuleType("timm.models")
+    layers = types.ModuleType("timm.models.layers")
+    registry = types.ModuleType("timm.models.registry")
+    layers.to_2tuple = lambda x: tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+    layers.trunc_normal_ = nn.init.trunc_normal_
+    layers.drop_path = lambda x, drop_prob=0.0, training=False: x
+    registry.register_model = lambda fn: fn
+    timm.models, models.layers, models.registry = models, layers, registry
+    sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers,
+                        "timm.models.registry": registry, "wget": types.ModuleType("wget")})
+
+
 def _randomise(module: nn.Module, seed: int):
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
@@ -132,6 +155,30 @@ def main():
     np.savez_compressed(OUT / "time_series_embed.npz", x=x.numpy(), y=y.numpy(),
                         w=de.value_embedding.tokenConv.weight.numpy())
     print("time_series_embed", tuple(y.shape))
+
+    # ---- AST tokenizer: the reference's PatchEmbed with the overlapping-stride conv ASTModel installs (:86) ----
+    _stub_timm()
+    ast_mod = _load_file_module("ref_ast_models", REF / "Audio/src/models/ast_models.py")
+    ape = ast_mod.PatchEmbed(img_size=224, patch_size=16, in_chans=1, embed_dim=64).eval()
+    ape.proj = nn.Conv2d(1, 64, kernel_size=(16, 16), stride=(10, 10))      # ast_models.py:86 (fstride = tstride = 10)
+    _randomise(ape, seed=5)
+    g = torch.Generator().manual_seed(17)
+    x = torch.randint(-8, 9, (2, 1, 64, 100), generator=g).float() / 8.0     # (B, 1, F, T) as built at :152-153
+    y = ape(x)
+    np.savez_compressed(OUT / "audio_patch_embed.npz", x=x.numpy().astype(np.float16), y=y.numpy(),
+                        w=ape.proj.weight.numpy(), b=ape.proj.bias.numpy(), stride=np.array([10, 10]))
+    print("audio_patch_embed", tuple(y.shape))
+
+    # ---- VideoMAE tubelet tokenizer ----
+    vid_mod = _load_file_module("ref_modeling_finetune", REF / "Video/models/modeling_finetune.py")
+    vpe = vid_mod.PatchEmbed(img_size=32, patch_size=16, in_chans=3, embed_dim=64, num_frames=4, tubelet_size=2).eval()
+    _randomise(vpe, seed=6)
+    g = torch.Generator().manual_seed(19)
+    x = torch.randint(-8, 9, (2, 3, 4, 32, 32), generator=g).float() / 8.0
+    y = vpe(x)
+    np.savez_compressed(OUT / "video_patch_embed.npz", x=x.numpy().astype(np.float16), y=y.numpy(),
+                        w=vpe.proj.weight.numpy(), b=vpe.proj.bias.numpy())
+    print("video_patch_embed", tuple(y.shape))
 
 
 if __name__ == "__main__":

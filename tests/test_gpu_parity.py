@@ -192,6 +192,28 @@ def test_image_tokenizer_matches_reference_golden(mt, golden_dir):
     _assert_close(y, torch.from_numpy(z["y"]), what="Image.PatchEmbed golden")
 
 
+def test_audio_and_video_tokenizers_match_reference_golden(mt, golden_dir):
+    """vectors produced by the reference's own PatchEmbed classes (tests/golden/make_golden.py)"""
+    z = np.load(golden_dir / "audio_patch_embed.npz")
+    tok = mt.data2seq.Acoustic.PatchEmbed(embed_dim=64, fstride=int(z["stride"][0]), tstride=int(z["stride"][1]))
+    tok.proj.weight.data.copy_(torch.from_numpy(z["w"]))
+    tok.proj.bias.data.copy_(torch.from_numpy(z["b"]))
+    tok = tok.cuda().eval()
+    with torch.no_grad():
+        y = tok(torch.from_numpy(z["x"].astype(np.float32)).cuda())
+    assert y.shape == (2, 45, 64)
+    _assert_close(y, torch.from_numpy(z["y"]), what="AST PatchEmbed golden")
+    z = np.load(golden_dir / "video_patch_embed.npz")
+    tok = mt.data2seq.Video.PatchEmbed(img_size=32, patch_size=16, embed_dim=64, num_frames=4, tubelet_size=2)
+    tok.proj.weight.data.copy_(torch.from_numpy(z["w"]))
+    tok.proj.bias.data.copy_(torch.from_numpy(z["b"]))
+    tok = tok.cuda().eval()
+    with torch.no_grad():
+        y = tok(torch.from_numpy(z["x"].astype(np.float32)).cuda())
+    assert y.shape == (2, 8, 64)
+    _assert_close(y, torch.from_numpy(z["y"]), what="VideoMAE PatchEmbed golden")
+
+
 def test_audio_and_video_tokenizers_match_oracle(mt):
     g = torch.Generator().manual_seed(5)
     with torch.no_grad():

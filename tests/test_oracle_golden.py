@@ -48,6 +48,22 @@ def test_image_patch_embed_matches_reference(golden_dir):
     assert (y - g["y"]).abs().max() < 1e-4
 
 
+def test_audio_patch_embed_matches_reference(golden_dir):
+    """AST tokenizer: the reference's PatchEmbed.forward with the stride-10 conv ASTModel installs (ast_models.py:18-33,86)"""
+    g = _load(golden_dir, "audio_patch_embed.npz")
+    y = orc.patch_embed_2d(g["x"].float(), g["w"], g["b"], tuple(int(v) for v in g["stride"]))
+    assert y.shape == g["y"].shape == (2, 45, 64)          # f = (64-16)//10+1 = 5, t = (100-16)//10+1 = 9
+    assert (y - g["y"]).abs().max() < 1e-4
+
+
+def test_video_patch_embed_matches_reference(golden_dir):
+    """VideoMAE tubelet tokenizer (Video/models/modeling_finetune.py:263-297)"""
+    g = _load(golden_dir, "video_patch_embed.npz")
+    y = orc.patch_embed_3d(g["x"].float(), g["w"], g["b"], (2, 16, 16))
+    assert y.shape == g["y"].shape == (2, 8, 64)
+    assert (y - g["y"]).abs().max() < 1e-4
+
+
 def test_time_series_embed_matches_reference(golden_dir):
     g = _load(golden_dir, "time_series_embed.npz")
     y = orc.time_series_embed(g["x"], g["w"])
