@@ -1,6 +1,7 @@
 """CPU oracle for Meta-Transformer's shared encoder path.  TEST INFRASTRUCTURE ONLY.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg may import this module;
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg (and bench.py's parity
+spot check, as the checker) may import this module;
 the product package (metatransformer_b200/) never does — it fails loudly when the CUDA extension is missing.
 
 What is restated (all arithmetic in plain torch CPU ops written out explicitly, float32 or float64):
@@ -18,10 +19,11 @@ PARITY PINNING.  The reference holds NO golden vector / known-answer test for th
 timm itself cannot be imported here.  The oracle is therefore pinned against outputs of the reference's OWN code
 run in the build container: tests/golden/make_golden.py executes the reference's in-tree Attention/Block/Mlp
 classes (attention.py / mlp.py loaded from /root/reference with their package-relative imports stubbed),
-Data2Seq/Image.py and Data2Seq/Time_Series.py on seeded inputs and stores the vectors in tests/golden/*.npz;
-tests/test_oracle_golden.py checks this file against them.  The audio / video tokenizers have no importable
-reference class (timm import at file top) and are pinned against torch.nn.functional.conv2d/conv3d instead —
-for those two functions parity is "unpinned against reference code, pinned against torch".
+Data2Seq/Image.py, Data2Seq/Time_Series.py and — with stand-ins for the `timm` / `wget` names their files import at
+module level — the PatchEmbed classes of Audio/src/models/ast_models.py and Video/models/modeling_finetune.py, on seeded
+inputs, and stores the vectors in tests/golden/*.npz; tests/test_oracle_golden.py checks this file against them.
+Also allowed to call this module, as a checker only: the two-sequence parity figure bench.py prints beside its
+throughput.  Status: every function below is pinned against reference code run here.
 """
 from __future__ import annotations
 
