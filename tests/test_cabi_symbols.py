@@ -61,3 +61,25 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setenv("MT_B200_LIB", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.MtError, match="no CPU / eager fallback"):
         _lib.load()
+
+
+def test_header_is_plain_c_and_product_never_imports_the_oracle(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (no C++ / torch types); and the product package must not
+    reference oracle/ anywhere (the oracle is test infrastructure)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    gcc = shutil.which("gcc")
+    if gcc:
+        src = tmp_path / "use_header.c"
+        src.write_text('#include "mt_b200.h"\n'
+                       "int probe(void) { mt_gemm_opts o; o.act = 0; mt_block_weights w; (void)w; (void)o;\n"
+                       "  return mt_version() + (int)MT_ERR_CUDA + (int)MT_DT_F16 + (int)MT_POOL_FIRST_TWO; }\n")
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", f"-I{root / 'include'}", str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    offenders = [str(p.relative_to(root)) for p in (root / "metatransformer_b200").rglob("*")
+                 if p.suffix in (".py", ".cu", ".cuh", ".h") and "lib" not in p.parts
+                 and ("from oracle" in p.read_text(errors="ignore") or "import oracle" in p.read_text(errors="ignore"))]
+    assert offenders == [], offenders
