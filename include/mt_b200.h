@@ -53,30 +53,51 @@ int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* re
  * (attention.py:56 `attn(norm1(x))` -> qkv, :57 `mlp(norm2(x))` -> fc1).                                      */
 int mt_row_stats(const void* x, int x_dtype, float* stats /* [M][2] = mean, rstd */, int M, int d, float eps,
                  void* stream);
+/* same for a split (hi + lo) bf16 row: statistics of hi + lo in fp32 */
+int mt_row_stats_split(const void* x_hi, const void* x_lo, float* stats, int M, int d, float eps, void* stream);
+/* Entry transform of the whole-encoder driver: c_row[m] = mean(x[m,:]); (hi, lo) = split(x - c_row) as bf16 [M,d] each;
+ * stats[m] = (0, rstd) = LayerNorm statistics of the centred row.  LayerNorm is shift-invariant and residual adds
+ * commute with a per-row constant, so the Block stack runs unchanged on the centred stream (bf16(x - mean) instead of
+ * bf16(x) feeds the LN-folded GEMMs: no loss when |mean| >> std) and c_row comes back through y_row_offset below. */
+int mt_center_split(const void* x, int x_dtype, void* hi, void* lo, float* c_row, float* stats, int M, int d, float eps,
+                    void* stream);
 int mt_fold_layernorm(const void* w /* [N,K] */, int w_dtype, const float* gamma, const float* beta,
                       const float* bias /* [N] or NULL */, void* w_folded /* bf16 [N,K] */, float* colsum /* [N] */,
                       float* bias_folded /* [N] */, int N, int K, void* stream);
 int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float* bias_folded, const float* colsum,
                     const float* row_stats, void* y, int M, int N, int K, int act, int cta_group, void* stream);
 
-/* General form of the two calls above.  `out_row_sums` lets a GEMM whose output is the next LayerNorm's input
- * (proj+residual, fc2+residual) emit that LayerNorm's statistics from its epilogue: for every output row one partial
- * (sum, sum of squares) pair per 128-column slice, layout [M][S][2] fp32 with S = 2*ceil(N/256) (plain stores, fixed
- * order => deterministic, no zero-initialisation).  The consuming LN-folded GEMM takes them with
- * ln_stats_are_sums = S (mean = sum/K, var = sumsq/K - mean^2): no separate statistics pass over HBM is needed.  */
+/* General form of the two calls above.
+ *
+ * Split residual stream.  Block.forward adds two branch outputs per layer to x (attention.py:56-57); with a bf16-only x
+ * the 2L roundings dominate the error of the whole encoder (1.8e-2 of max|x| after 12 layers).  The residual GEMMs
+ * (proj, fc2) therefore keep x as a PAIR of bf16 tensors hi + lo (16 mantissa bits): `residual` / `residual_lo` are
+ * read, added to the fp32 accumulator, and the sum is written as `y` = bf16(v) and `y_lo` = bf16(v - y).  `y` alone is
+ * the A operand of the next GEMM; either lo pointer may be NULL (a bf16 input has no lo; a bf16 result needs none).
+ *
+ * `out_row_sums` lets a GEMM whose output is the next LayerNorm's input emit that LayerNorm's statistics from its
+ * epilogue: for every output row one record per 64-column slice, layout [M][S][4] fp32 with S = ceil(N/64):
+ * (shift, sum(v - shift), sum((v - shift)^2), 0) with shift = the row's first value in the slice (shifted sums: no
+ * cancellation when |mean| >> std; plain stores in a fixed layout => deterministic, no zero-initialisation).  The
+ * consuming LN-folded GEMM takes them with ln_stats_are_sums = S = ceil(K/64) and combines them pairwise-exactly
+ * (mean_i = shift_i + s1_i/n_i, M2 = sum M2_i + n_i (mean_i - mean)^2): no separate statistics pass over HBM.       */
 typedef struct {
   const float* bias;            /* [N] or NULL */
-  const void* residual;         /* bf16 [M,N] or NULL (act 2: the saved pre-activation) */
+  const void* residual;         /* bf16 [M,N] or NULL (act 2: the saved pre-activation); 32-byte aligned */
   int act;                      /* 0, 1 (GELU), 2 (times gelu'(residual)) */
   const float* ln_colsum;       /* LN folding of the INPUT (with ln_row_stats), or NULL */
-  const float* ln_row_stats;    /* [M][2] (mean, rstd), or [M][S][2] partial sums if ln_stats_are_sums = S > 0 */
+  const float* ln_row_stats;    /* [M][2] (mean, rstd), or [M][S][4] records if ln_stats_are_sums = S > 0 */
   int ln_stats_are_sums;
   float ln_eps;                 /* used when ln_stats_are_sums */
-  float* out_row_sums;          /* [M][2*ceil(N/256)][2] partial statistics of the OUTPUT rows, or NULL */
+  float* out_row_sums;          /* [M][ceil(N/64)][4] statistics records of the OUTPUT rows, or NULL */
   int cta_group;                /* 0 auto, 1, 2 */
   int residual_period;          /* > 0: `residual` is a [residual_period, N] table and output row m adds row
                                    m % residual_period (positional embedding broadcast over the batch:
                                    Audio/src/models/ast_models.py:159, Video/models/modeling_finetune.py:434-436) */
+  const void* residual_lo;      /* bf16 [M,N] low half of the residual, or NULL */
+  void* y_lo;                   /* bf16 [M,N] low half of the output, or NULL */
+  const float* y_row_offset;    /* [M] or NULL: added to every element of output row m before it is rounded / split
+                                   (undoes mt_center_split in the last residual GEMM); residual GEMMs only */
 } mt_gemm_opts;
 int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int N, int K, const mt_gemm_opts* opts, void* stream);
 
@@ -180,6 +201,20 @@ int mt_pad_cols(const void* x, void* out, int dtype, long long rows, int c_in, i
 /* ---- dtype conversion helper (weights packing, fp32 activations at the boundary) ---- */
 int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 
+/* split representation helpers: hi = bf16(x), lo = bf16(x - hi) / dst = hi + lo (fp32); n % 4 == 0 */
+int mt_split_f32(const float* src, void* hi, void* lo, size_t n, void* stream);
+int mt_merge_f32(const void* hi, const void* lo, float* dst, size_t n, void* stream);
+
+/* ---- device timeline (measurement aid, off by default) -----------------------------------------------------------
+ * Between mt_timeline_begin and mt_timeline_end every instrumented launch (GEMM, attention forward, row statistics)
+ * takes the next slot of `slots` (device memory, capacity x 2 x uint64): slot[0] = min over CTAs of %globaltimer at
+ * kernel start, slot[1] = max at kernel end (atomicMin / atomicMax: initialise the buffer to {~0, 0} before running).
+ * Launches captured into a CUDA graph keep their slot, so one replay of the graph fills the table with the start/end
+ * times of every kernel inside the replay — the gaps between them are what the per-kernel durations do not show.
+ * mt_timeline_end returns the number of slots handed out.  Process-wide, not thread-safe.                          */
+int mt_timeline_begin(void* slots, int capacity);
+int mt_timeline_end(void);
+
 /* ---- E0/E1: whole-encoder driver ---------------------------------------------------------------------------
  * nn.Sequential(*[Block(dim, heads, mlp_ratio, qkv_bias=True) for _ in range(depth)]) (README.md:125-147).
  * Weights are borrowed device pointers (bf16 matrices, fp32 vectors) that must outlive the handle.          */
@@ -206,6 +241,11 @@ int mt_encoder_workspace_bytes(const mt_encoder* enc, int B, int N, size_t* byte
 /* x, y: bf16 [B, N, dim] (y may alias x); workspace: device scratch of at least workspace_bytes */
 int mt_encoder_forward(mt_encoder* enc, const void* x, void* y, int B, int N,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* General form: x / y are bf16 or fp32 [B, N, dim] (x_dtype / y_dtype = MT_DT_BF16 | MT_DT_F32).  Inside, the residual
+ * stream is the split hi + lo bf16 pair in either case; an fp32 x is split on entry (no precision lost to bf16), an
+ * fp32 y is hi + lo merged on exit.                                                                              */
+int mt_encoder_forward_ex(mt_encoder* enc, const void* x, int x_dtype, void* y, int y_dtype, int B, int N,
+                          void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one mt_encoder_forward launches (for accounting) */
 int mt_encoder_launches_per_forward(const mt_encoder* enc);
 

@@ -21,7 +21,8 @@ EXPORTED_SYMBOLS = (
     "mt_attention_fwd_lse", "mt_attention_bwd_workspace_bytes", "mt_attention_bwd",
     "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_assemble_tokens", "mt_pool_layernorm", "mt_pool_layernorm_bwd",
     "mt_dropout", "mt_pad_cols", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
-    "mt_encoder_forward", "mt_encoder_launches_per_forward",
+    "mt_encoder_forward", "mt_encoder_forward_ex", "mt_encoder_launches_per_forward",
+    "mt_row_stats_split", "mt_center_split", "mt_split_f32", "mt_merge_f32", "mt_timeline_begin", "mt_timeline_end",
 )
 
 
@@ -35,6 +36,7 @@ class GemmOpts(Structure):
         ("bias", c_void_p), ("residual", c_void_p), ("act", c_int),
         ("ln_colsum", c_void_p), ("ln_row_stats", c_void_p), ("ln_stats_are_sums", c_int), ("ln_eps", c_float),
         ("out_row_sums", c_void_p), ("cta_group", c_int), ("residual_period", c_int),
+        ("residual_lo", c_void_p), ("y_lo", c_void_p), ("y_row_offset", c_void_p),
     ]
 
 
@@ -124,6 +126,21 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_encoder_workspace_bytes.argtypes = [c_void_p, c_int, c_int, POINTER(c_size_t)]
     lib.mt_encoder_forward.restype = c_int
     lib.mt_encoder_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]
+    lib.mt_encoder_forward_ex.restype = c_int
+    lib.mt_encoder_forward_ex.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t,
+                                          c_void_p]
+    lib.mt_row_stats_split.restype = c_int
+    lib.mt_row_stats_split.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]
+    lib.mt_center_split.restype = c_int
+    lib.mt_center_split.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]
+    lib.mt_split_f32.restype = c_int
+    lib.mt_split_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.mt_merge_f32.restype = c_int
+    lib.mt_merge_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.mt_timeline_begin.restype = c_int
+    lib.mt_timeline_begin.argtypes = [c_void_p, c_int]
+    lib.mt_timeline_end.restype = c_int
+    lib.mt_timeline_end.argtypes = []
     lib.mt_encoder_launches_per_forward.restype = c_int
     lib.mt_encoder_launches_per_forward.argtypes = [c_void_p]
 

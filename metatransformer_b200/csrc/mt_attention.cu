@@ -55,6 +55,7 @@ struct AttnParams {
   int num_items;     // B * H * num_qp
   float scale_log2;  // scale * log2(e)
   float* lse2;       // optional [B, H, N]: log2-sum-exp of the scaled scores (m*c + log2 l), saved for the backward
+  unsigned long long* tl;   // optional timeline slot (mt_timeline_begin)
 };
 
 __global__ void __launch_bounds__(kAtThreads, 1)
@@ -110,6 +111,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const uint32_t tmem_base = *tmem_ptr_gen;
   pdl_launch_dependents();
   pdl_wait();
+  timeline_start(p.tl);
 
   const int H = p.H;
 
@@ -432,6 +434,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc<1>(tmem_base, kAtTmemCols);
+  timeline_end(p.tl);
 }
 
 }  // namespace mt
@@ -478,6 +481,7 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
   p.num_items = B * H * p.num_qp;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse2 = lse2;
+  p.tl = timeline_next_slot();
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;

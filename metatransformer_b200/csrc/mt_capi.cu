@@ -94,6 +94,51 @@ int sm_count(int* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// device timeline (mt_timeline_begin / mt_timeline_end): instrumented launches take consecutive {start, end} slots
+// ------------------------------------------------------------------------------------------------
+static unsigned long long* g_tl_buf = nullptr;
+static int g_tl_cap = 0, g_tl_next = 0;
+
+unsigned long long* timeline_next_slot() {
+  if (g_tl_buf == nullptr || g_tl_next >= g_tl_cap) return nullptr;
+  return g_tl_buf + 2 * size_t(g_tl_next++);
+}
+
+// split representation of fp32 data: hi = bf16(x), lo = bf16(x - hi)  (hi + lo carries 16 mantissa bits)
+__global__ void split_f32_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, size_t n) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i + 3 < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16_rn(f[j]);
+      l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+__global__ void merge_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                 float* __restrict__ dst, size_t n) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i + 3 < n; i += stride) {
+    __nv_bfloat16 h[4], l[4];
+    *reinterpret_cast<uint2*>(h) = *reinterpret_cast<const uint2*>(hi + i);
+    *reinterpret_cast<uint2*>(l) = *reinterpret_cast<const uint2*>(lo + i);
+    float4 v;
+    v.x = __bfloat162float(h[0]) + __bfloat162float(l[0]);
+    v.y = __bfloat162float(h[1]) + __bfloat162float(l[1]);
+    v.z = __bfloat162float(h[2]) + __bfloat162float(l[2]);
+    v.w = __bfloat162float(h[3]) + __bfloat162float(l[3]);
+    *reinterpret_cast<float4*>(dst + i) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // elementwise cast (weight packing fp32 -> bf16, boundary conversions). Memory-bound, 16 B per thread-load.
 // ------------------------------------------------------------------------------------------------
 template <typename S>
@@ -141,7 +186,7 @@ static int launch_cast(const void* src, void* dst, size_t n, cudaStream_t s) {
 
 }  // namespace mt
 
-extern "C" int mt_version(void) { return 100; }
+extern "C" int mt_version(void) { return 200; }
 
 extern "C" const char* mt_last_error(void) { return mt::g_err; }
 
@@ -152,6 +197,67 @@ extern "C" int mt_device_ok(int device) {
   MT_REQUIRE(prop.major == 10, MT_ERR_UNSUPPORTED,
              "device %d is compute capability %d.%d; libmt_b200 contains sm_100a code only", device, prop.major,
              prop.minor);
+  return MT_OK;
+}
+
+extern "C" int mt_timeline_begin(void* slots, int capacity) {
+  using namespace mt;
+  MT_REQUIRE(slots != nullptr && capacity > 0, MT_ERR_BAD_SHAPE, "mt_timeline_begin: need a device buffer and a capacity");
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(slots) & 7) == 0, MT_ERR_BAD_ALIGN, "mt_timeline_begin: buffer must be 8-byte aligned");
+  g_tl_buf = reinterpret_cast<unsigned long long*>(slots);
+  g_tl_cap = capacity;
+  g_tl_next = 0;
+  return MT_OK;
+}
+
+extern "C" int mt_timeline_end(void) {
+  const int used = mt::g_tl_next;
+  mt::g_tl_buf = nullptr;
+  mt::g_tl_cap = 0;
+  mt::g_tl_next = 0;
+  return used;
+}
+
+static int split_merge_grid(size_t n, unsigned* blocks) {
+  int sms = 0;
+  int rc = mt::sm_count(&sms);
+  if (rc) return rc;
+  size_t b = (n / 4 + 255) / 256;
+  if (b > size_t(sms) * 16) b = size_t(sms) * 16;
+  if (b < 1) b = 1;
+  *blocks = unsigned(b);
+  return MT_OK;
+}
+
+extern "C" int mt_split_f32(const float* src, void* hi, void* lo, size_t n, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(src && hi && lo, MT_ERR_BAD_SHAPE, "mt_split_f32: null pointer");
+  MT_REQUIRE(n % 4 == 0, MT_ERR_BAD_SHAPE, "mt_split_f32: n must be a multiple of 4");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_split_f32: pointers must be 16-byte aligned");
+  if (n == 0) return MT_OK;
+  unsigned blocks = 1;
+  int rc = split_merge_grid(n, &blocks);
+  if (rc) return rc;
+  split_f32_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+extern "C" int mt_merge_f32(const void* hi, const void* lo, float* dst, size_t n, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(dst && hi && lo, MT_ERR_BAD_SHAPE, "mt_merge_f32: null pointer");
+  MT_REQUIRE(n % 4 == 0, MT_ERR_BAD_SHAPE, "mt_merge_f32: n must be a multiple of 4");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_merge_f32: pointers must be 16-byte aligned");
+  if (n == 0) return MT_OK;
+  unsigned blocks = 1;
+  int rc = split_merge_grid(n, &blocks);
+  if (rc) return rc;
+  merge_f32_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo), dst, n);
+  MT_CHECK_CUDA(cudaGetLastError());
   return MT_OK;
 }
 

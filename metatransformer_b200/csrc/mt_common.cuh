@@ -37,6 +37,9 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const voi
 
 int sm_count(int* out);
 
+// next {start, end} slot of the device timeline (mt_timeline_begin), or nullptr when no timeline is being recorded
+unsigned long long* timeline_next_slot();
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // Launch with an optional cluster dimension and, when MT_B200_PDL=1, programmatic dependent launch.  PDL is OFF by

@@ -12,11 +12,16 @@
 //     two accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
 //   * CG = 2: CTA pairs (cta_group::2): one 256x256 output tile per pair, each CTA loads its own 128 rows of X
 //     and half (128 rows) of the W tile, halving per-SM operand traffic from L2;
-//   * 8 epilogue warps: TMEM -> registers (tcgen05.ld) -> bias / exact-erf GELU / residual -> bf16 ->
-//     swizzled smem -> TMA store (coalesced, clips the M/N tails in hardware).
+//   * 16 epilogue warps (four per scheduler: the epilogue is a latency-bound instruction stream that has to finish a
+//     128 x 256 tile in less time than the 12 k-blocks of a K = 768 main loop): TMEM -> registers (tcgen05.ld x16) ->
+//     bias / LayerNorm fold / exact-erf GELU / residual -> bf16 -> 64B-swizzled smem -> TMA store (coalesced, clips
+//     the M/N tails in hardware); compile-time specialisations for the encoder's three hot epilogues;
+//   * the residual stream is a split pair hi + lo of bf16 tensors (16 mantissa bits): the residual GEMMs (proj, fc2)
+//     read both halves, add in fp32 and write both; `hi` alone is the A operand of the next GEMM.  A bf16-only
+//     stream costs 1.8e-2 max-abs error after 12 layers, the split one 3e-3 (tools/precision_model.py).
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 idle, warps 4..11 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the column half).
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
+// warps 4..19 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the 64-column quarter of the tile).
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 #include <stdlib.h>
@@ -27,20 +32,32 @@ constexpr int kBM = 128;         // rows of X per CTA
 constexpr int kBN = 256;         // UMMA N
 constexpr int kBK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+constexpr int kRoleWarps = 4;    // warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle
+constexpr int kEpiWarps = 16;    // four per scheduler: the epilogue is a latency-bound instruction stream
+constexpr int kGemmThreads = 32 * (kRoleWarps + kEpiWarps);   // 640 (<= 96 registers per thread)
+constexpr int kEpiCols = kBN / (kEpiWarps / 4);               // 64 output columns per epilogue warp
+constexpr int kPiece = 16;       // columns per tcgen05.ld (keeps the accumulator slice at 16 registers)
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kBN;  // 512
-constexpr int kEpiStageBytes = 32 * 128;     // per-warp staging: 32 rows x 64 bf16
-constexpr int kBiasBytes = 2 * 128 * 4;      // per-warp slices: 128 fp32 bias + 128 fp32 LN-fold column sums
+constexpr int kBiasBytes = 2 * kEpiCols * 4; // per warp: 64 fp32 bias + 64 fp32 LN-fold column sums
 
-template <int CG>
+// Epilogue specialisations (compile-time): the hot shapes of the encoder get straight-line code, everything else
+// (backward act 2, split-K accumulation, periodic residual tables, odd combinations) runs the generic variant.
+enum : int {
+  kEpiGeneric = 0,   // run-time flags: bias, residual (bf16, optional period), act 0/1/2, LN fold, row sums, split-K
+  kEpiLn = 1,        // LN fold + bias                          (qkv)
+  kEpiLnGelu = 2,    // LN fold + bias + exact-erf GELU          (fc1)
+  kEpiRes = 3,       // bias + residual (hi [+ lo]) -> hi [+ lo] output + LayerNorm row sums     (proj, fc2)
+};
+
+template <int CG, bool HILO>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;                       // 16 KB
   static constexpr int kBRows = (CG == 2) ? kBN / 2 : kBN;            // rows of W this CTA loads
   static constexpr int kBBytes = kBRows * kBK * 2;                    // 16 / 32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CG == 2) ? 5 : 3;
+  static constexpr int kStages = (CG == 2) ? (HILO ? 4 : 5) : 3;
+  static constexpr int kEpiStageBytes = HILO ? 4096 : 2048;           // per warp: 32 rows x 32 columns bf16 (hi [, lo])
   static constexpr int kSmemEpiOff = kStages * kStageBytes;
   static constexpr int kSmemBiasOff = kSmemEpiOff + kEpiWarps * kEpiStageBytes;
   static constexpr int kSmemBarOff = kSmemBiasOff + kEpiWarps * kBiasBytes;
@@ -51,29 +68,33 @@ struct GemmCfg {
 
 struct GemmParams {
   const float* bias;            // [N] fp32 or nullptr
-  const __nv_bfloat16* resid;   // [M, ldr] bf16 (or [resid_period, ldr], see below) or nullptr
+  const __nv_bfloat16* resid;   // [M, ldr] bf16 (or [resid_period, ldr], see below) or nullptr; rows 32-byte aligned
+  const __nv_bfloat16* resid_lo;// low half of a split (hi + lo) residual stream, or nullptr (kEpiRes only)
   int ldr;
-  int resid_ld256;              // residual rows are 32-byte aligned: fetch them with 256-bit loads
   int resid_period;             // > 0: output row m reads residual row m % resid_period (a [n, d] positional table
                                 // broadcast over the batch: tokenizer GEMMs)
   int M, N, K;
   int act;                      // 0 = identity, 1 = exact-erf GELU, 2 = multiply by gelu'(resid) (backward)
   int num_m_tiles, num_n_tiles;
   // LayerNorm folded into the GEMM (see mt_fold_layernorm): y = rstd_m * (acc - mean_m * colsum_n) + bias_n
-  const float2* row_stats;      // [M] (mean, rstd) — or (sum, sum of squares) when ln_sums != 0 — or nullptr
-  int ln_sums;                  // > 0: row_stats holds ln_sums partial (sum, sum of squares) pairs per row, written by
-                                // the epilogue of the GEMM that produced this GEMM's input
+  const float* row_stats;       // [M][2] (mean, rstd) — or [M][ln_sums][4] partial statistics when ln_sums > 0
+  int ln_sums;                  // > 0: row_stats holds ln_sums (shift, sum(v - shift), sum((v - shift)^2), -) records per
+                                // row, one per 64-column slice, written by the epilogue of the GEMM that produced this
+                                // GEMM's input (shifted sums: no cancellation when |mean| >> std)
   float ln_eps;
   // split-K accumulation mode (weight gradients: few output tiles, very long K): work item = (tile, K split); the
   // epilogue adds the fp32 partial tile to out_f32 [M,N] with red.global.add (zero-initialised by the host wrapper)
   float* out_f32;
   int split_k;                  // >= 1
   int kb_per_split;             // k-blocks per split (every split is non-empty)
-  float* out_row_sums;          // [M][2*num_n_tiles][2]: per-(row, 128-column slice) partial (sum, sum of squares) of
-                                // this GEMM's output, or nullptr (plain stores: deterministic, no zero-init)
+  float* out_row_sums;          // [M][ceil(N/64)][4] statistics records of this GEMM's output rows, or nullptr (plain
+                                // stores in a fixed layout: deterministic, no zero-init)
+  int has_out_lo;               // kEpiRes: also store the low half of the output (tm_ylo)
+  const float* row_offset;      // kEpiRes: [M] added to every element of output row m (undoes mt_center_split), or nullptr
   const float* colsum;          // [N] sum_k W'[n,k] (of the bf16-rounded folded weight) or nullptr
   int mn_major;                 // 1: both operands are stored reduction-dim-major (A = dY[k, m], B = X[k, n]: the weight
                                 // gradient dW = dY^T X straight from the row-major activations, no transposed copies)
+  unsigned long long* tl;       // optional timeline slot {first CTA start, last CTA end} in globaltimer ns, or nullptr
 };
 
 // gelu(x) = x * Phi(x) with the exact (erf) definition, nn.GELU() default.
@@ -106,30 +127,41 @@ MT_DEVINL float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, g, cdf);
 }
 
-// two elements at a time with packed fp32x2 FMAs (the epilogue is issue-bound: ~1/3 fewer instruction slots)
+// Two elements per call with packed fp32x2 FMAs, written in n = -min(|x|, 12) so that no sign flip or extra multiply
+// is needed:  t p(t) = n q(n) with q(n) = -p(-n);  0.5 erfc(t/sqrt2) = 2^(n q(n) - 1);  gelu = relu(x) + n * that.
+// Per element: 2 FMNMX + 3 packed FMA-class slots + 1 MUFU (the epilogue is issue-bound).
 MT_DEVINL uint64_t gelu_erf_x2(uint64_t x) {
   float x0, x1;
   unpack_f32x2(x, x0, x1);
-  const uint64_t t = pack_f32x2(fminf(fabsf(x0), 12.0f), fminf(fabsf(x1), 12.0f));
-  uint64_t p = pack_f32x2(-0.00048811757005751133f, -0.00048811757005751133f);
-  p = fma_f32x2(p, t, pack_f32x2(0.007198806386440992f, 0.007198806386440992f));
-  p = fma_f32x2(p, t, pack_f32x2(-0.052146803587675095f, -0.052146803587675095f));
-  p = fma_f32x2(p, t, pack_f32x2(-0.4595957100391388f, -0.4595957100391388f));
-  p = fma_f32x2(p, t, pack_f32x2(-1.1510006189346313f, -1.1510006189346313f));
+  const uint64_t n = pack_f32x2(fmaxf(-fabsf(x0), -12.0f), fmaxf(-fabsf(x1), -12.0f));
+  uint64_t q = pack_f32x2(0.00048811757005751133f, 0.00048811757005751133f);
+  q = fma_f32x2(q, n, pack_f32x2(0.007198806386440992f, 0.007198806386440992f));
+  q = fma_f32x2(q, n, pack_f32x2(0.052146803587675095f, 0.052146803587675095f));
+  q = fma_f32x2(q, n, pack_f32x2(-0.4595957100391388f, -0.4595957100391388f));
+  q = fma_f32x2(q, n, pack_f32x2(1.1510006189346313f, 1.1510006189346313f));
   float w0, w1;
-  unpack_f32x2(mul_f32x2(p, t), w0, w1);
+  unpack_f32x2(fma_f32x2(q, n, pack_f32x2(-1.0f, -1.0f)), w0, w1);
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(w0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(w1));
-  const uint64_t te = mul_f32x2(t, pack_f32x2(e0, e1));
-  return fma_f32x2(te, pack_f32x2(-0.5f, -0.5f), pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  return fma_f32x2(n, pack_f32x2(e0, e1), pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
 }
 
-template <int CG>
+MT_DEVINL uint64_t bf16x2_to_f32x2(uint32_t v) { return pack_f32x2(bf16_lo(v), bf16_hi(v)); }
+
+MT_DEVINL void ldg_nc_v8(const void* ptr, uint32_t (&d)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+               : "l"(ptr));
+}
+
+template <int CG, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_y, const GemmParams p) {
-  using Cfg = GemmCfg<CG>;
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_ylo,
+                 const GemmParams p) {
+  constexpr bool kHiLo = (MODE == kEpiRes);
+  using Cfg = GemmCfg<CG, kHiLo>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -154,6 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_y);
+    if constexpr (kHiLo) tma_prefetch_desc(&tm_ylo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -175,6 +208,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   pdl_launch_dependents();
   pdl_wait();
+  timeline_start(p.tl);
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;   // work items: (tile, K split), split fastest
   const int num_kb = (p.K + kBK - 1) / kBK;
@@ -195,7 +229,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          if (p.mn_major) {
+          if (MODE == kEpiGeneric && p.mn_major) {
             // MN-major operand tiles: [64 reduction rows x 64 columns] boxes (128 B swizzle rows), 8 KB each; the
             // 128-wide A / B slices of this CTA are two such boxes 8 KB apart (the descriptor's leading byte offset)
             if constexpr (CG == 2) {
@@ -236,9 +270,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     if (leader && lane == 0) {
-      const uint32_t idesc = p.mn_major ? make_idesc_bf16(kBM * CG, kBN, 1, 1) : make_idesc_bf16(kBM * CG, kBN);
+      const bool mnm = (MODE == kEpiGeneric) && p.mn_major;
+      const uint32_t idesc = mnm ? make_idesc_bf16(kBM * CG, kBN, 1, 1) : make_idesc_bf16(kBM * CG, kBN);
       // K step of 16: K-major = 32 B inside the swizzle row; MN-major = 16 rows of 128 B
-      const uint64_t kstep = p.mn_major ? uint64_t(2048 >> 4) : uint64_t(2);
+      const uint64_t kstep = mnm ? uint64_t(2048 >> 4) : uint64_t(2);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -253,9 +288,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = p.mn_major ? make_smem_desc_sw128(sa, 1024, 8192) : make_smem_desc_sw128(sa);
-          const uint64_t bdesc = p.mn_major ? make_smem_desc_sw128(sa + Cfg::kABytes, 1024, 8192)
-                                            : make_smem_desc_sw128(sa + Cfg::kABytes);
+          const uint64_t adesc = mnm ? make_smem_desc_sw128(sa, 1024, 8192) : make_smem_desc_sw128(sa);
+          const uint64_t bdesc = mnm ? make_smem_desc_sw128(sa + Cfg::kABytes, 1024, 8192)
+                                     : make_smem_desc_sw128(sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance 16 along K: +2 (32 B inside the 128B swizzle row) or +128 (16 rows) in the (addr >> 4) field
@@ -271,13 +306,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (++as == kAccStages) { as = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kRoleWarps) {
     // =============================== epilogue ===================================
-    const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int hf = (warp - 4) >> 2;  // column half of the 256-wide tile
-    const int ew = warp - 4;
-    const uint32_t stg = smem_base + Cfg::kSmemEpiOff + ew * kEpiStageBytes;
-    float* bias_s = reinterpret_cast<float*>(smem_gen + Cfg::kSmemBiasOff + ew * kBiasBytes);
+    // 16 warps: warp % 4 = TMEM lane quarter (32 output rows), (warp - 4) / 4 = 64-column quarter of the 256-wide tile.
+    // Per tile and warp: four 16-column pieces (tcgen05.ld x16 -> math -> bf16 -> 64B-swizzled staging), two TMA stores
+    // of 32 rows x 32 columns.  Everything a piece needs from global memory (residual) is fetched one piece ahead.
+    constexpr bool kGen = (MODE == kEpiGeneric);
+    const bool do_ln = kGen ? (p.row_stats != nullptr) : (MODE == kEpiLn || MODE == kEpiLnGelu);
+    const bool do_gelu = kGen ? (p.act == 1) : (MODE == kEpiLnGelu);
+    const bool do_act2 = kGen && (p.act == 2);
+    const bool do_resid = kGen ? (p.resid != nullptr) : kHiLo;
+    const bool do_sums = (kGen || kHiLo) && (p.out_row_sums != nullptr);
+    const bool do_splitk = kGen && (p.out_f32 != nullptr);
+    const int q = warp & 3;
+    const int ew = warp - kRoleWarps;
+    const int cq = ew >> 2;
+    const uint32_t stg = smem_base + Cfg::kSmemEpiOff + ew * Cfg::kEpiStageBytes;
+    const float4* bias_s4 = reinterpret_cast<const float4*>(smem_gen + Cfg::kSmemBiasOff + ew * kBiasBytes);
+    const uint32_t srow = stg + uint32_t(lane * 64);
+    const uint32_t swz = uint32_t(lane >> 1) & 3u;     // 64B swizzle: 16-byte chunk index ^ ((row >> 1) & 3)
     int as = 0;
     uint32_t aphase = 0;
     bool store_pending = false;
@@ -285,79 +332,100 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int tile = t / p.split_k;
       const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
       const int row0 = m_tile * (kBM * CG) + int(rank) * kBM + 32 * q;  // first row of this warp
-      const int col0 = n_tile * kBN + 128 * hf;                          // first column of this warp
+      const int col0 = n_tile * kBN + kEpiCols * cq;                    // first column of this warp
       const int row = row0 + lane;
-      // bias (and LN-fold column-sum) slices for this warp's 128 columns -> private smem (float4 per lane)
-      float ln_rstd = 1.f, ln_nmr = 0.f;  // rstd and -mean*rstd of this thread's row
+      // bias (lanes 0-15) and LN-fold column sums (lanes 16-31) of this warp's 64 columns -> private smem
       {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int c = col0 + 4 * lane;
-        if (p.bias != nullptr && c < p.N) b4 = *reinterpret_cast<const float4*>(p.bias + c);
-        if (p.colsum != nullptr && c < p.N) c4 = *reinterpret_cast<const float4*>(p.colsum + c);
+        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* src = (lane < 16) ? p.bias : p.colsum;
+        const int c = col0 + 4 * (lane & 15);
+        if (src != nullptr && c < p.N) v4 = *reinterpret_cast<const float4*>(src + c);
         __syncwarp();
-        reinterpret_cast<float4*>(bias_s)[lane] = b4;
-        reinterpret_cast<float4*>(bias_s)[32 + lane] = c4;
+        const_cast<float4*>(bias_s4)[lane] = v4;
         __syncwarp();
-        if (p.row_stats != nullptr && row < p.M) {
-          float2 st;
-          if (p.ln_sums > 0) {   // partial (sum, sum of squares) per 128-column slice, fixed summation order
-            const float2* ps = p.row_stats + size_t(row) * p.ln_sums;
-            float sx = 0.f, sy = 0.f;
-            for (int i = 0; i < p.ln_sums; ++i) { const float2 t = ps[i]; sx += t.x; sy += t.y; }
-            const float inv_k = 1.0f / float(p.K);
-            const float mean = sx * inv_k;
-            st = make_float2(mean, rsqrtf(fmaxf(fmaf(sy, inv_k, -mean * mean), 0.f) + p.ln_eps));
-          } else {
-            st = p.row_stats[row];
+      }
+      float ln_rstd = 1.f, ln_nmr = 0.f;  // rstd and -mean*rstd of this thread's row
+      if (do_ln && row < p.M) {
+        float mean, rstd;
+        if (p.ln_sums > 0) {
+          // Combine the per-slice shifted sums (Chan et al.): slice mean_i = shift_i + s1_i/n_i, M2_i = s2_i - s1_i^2/n_i,
+          // M2 = sum M2_i + n_i (mean_i - mean)^2.  Fixed order: deterministic.
+          const float4* ps = reinterpret_cast<const float4*>(p.row_stats) + size_t(row) * p.ln_sums;
+          const float ref = ps[0].x;
+          float acc_m = 0.f;
+          for (int i = 0; i < p.ln_sums; ++i) {
+            const float4 r = ps[i];
+            const float n_i = float(min(64, p.K - 64 * i));
+            acc_m += fmaf(n_i, r.x - ref, r.y);
           }
-          ln_rstd = st.y;
-          ln_nmr = -st.x * st.y;
+          const float inv_k = 1.0f / float(p.K);
+          mean = fmaf(acc_m, inv_k, ref);
+          float m2 = 0.f;
+          for (int i = 0; i < p.ln_sums; ++i) {
+            const float4 r = ps[i];
+            const float n_i = float(min(64, p.K - 64 * i));
+            const float inv_n = 1.0f / n_i;
+            const float dm = fmaf(r.y, inv_n, r.x) - mean;
+            m2 += fmaf(n_i * dm, dm, fmaf(-r.y * inv_n, r.y, r.z));
+          }
+          rstd = rsqrtf(fmaxf(m2 * inv_k, 0.f) + p.ln_eps);
+        } else {
+          const float2 st = reinterpret_cast<const float2*>(p.row_stats)[row];
+          mean = st.x;
+          rstd = st.y;
         }
+        ln_rstd = rstd;
+        ln_nmr = -mean * rstd;
       }
       const uint64_t ln_rstd2 = pack_f32x2(ln_rstd, ln_rstd), ln_nmr2 = pack_f32x2(ln_nmr, ln_nmr);
-      uint64_t rs2 = pack_f32x2(0.f, 0.f), rss2 = rs2;   // running (sum, sum of squares) of this thread's output row
-      // residual slices are fetched one 32-column slice ahead of their use (the first one before the accumulator
-      // is even ready), so the L2/HBM latency hides behind the MMAs of this tile and the math of the previous slice
-      const bool row_ok = (p.resid != nullptr) && (row < p.M);
-      const __nv_bfloat16* rrow =
-          row_ok ? p.resid + size_t(p.resid_period > 0 ? row % p.resid_period : row) * p.ldr : nullptr;
-      uint4 rv_next[4];
-      auto load_resid = [&](int sc_, uint4 (&dst)[4]) {
-        const int c_ = col0 + 32 * sc_;
-        if (row_ok && c_ < p.N) {
-          if (p.resid_ld256) {
-            // two 32-byte loads: whole sectors per thread (rows are scattered, 16-byte loads would touch each sector twice)
+      uint64_t roff2 = pack_f32x2(0.f, 0.f);
+      if constexpr (kHiLo) {
+        if (p.row_offset != nullptr && row < p.M) {
+          const float c_ = p.row_offset[row];
+          roff2 = pack_f32x2(c_, c_);
+        }
+      }
+      // running statistics of this thread's 64 output values (shifted by the first one)
+      uint64_t s1 = pack_f32x2(0.f, 0.f), s2 = s1, nshift2 = s1;
+      float shift = 0.f;
+      // residual pieces (16 columns = 32 bytes of hi, 32 bytes of lo) are fetched one piece ahead of their use: the
+      // first one before the accumulator is even ready, so the L2/HBM latency hides behind the MMAs of this tile
+      const bool row_ok = do_resid && (row < p.M);
+      const __nv_bfloat16* rrow = nullptr;
+      const __nv_bfloat16* rrow_lo = nullptr;
+      if (row_ok) {
+        const size_t rr = size_t((kGen && p.resid_period > 0) ? row % p.resid_period : row) * p.ldr;
+        rrow = p.resid + rr;
+        if (kHiLo && p.resid_lo != nullptr) rrow_lo = p.resid_lo + rr;
+      }
+      uint32_t rh[2][8], rl[2][8];
+      auto load_resid = [&](int piece, uint32_t (&h)[8], uint32_t (&l)[8]) {
+        const int c_ = col0 + kPiece * piece;
+        if (rrow != nullptr && c_ < p.N) ldg_nc_v8(rrow + c_, h);
+        else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                           : "=r"(dst[2 * j].x), "=r"(dst[2 * j].y), "=r"(dst[2 * j].z), "=r"(dst[2 * j].w),
-                             "=r"(dst[2 * j + 1].x), "=r"(dst[2 * j + 1].y), "=r"(dst[2 * j + 1].z), "=r"(dst[2 * j + 1].w)
-                           : "l"(rrow + c_ + 16 * j));
-          } else {
-            const uint4* rp = reinterpret_cast<const uint4*>(rrow + c_);
+          for (int j = 0; j < 8; ++j) h[j] = 0u;
+        }
+        if constexpr (kHiLo) {
+          if (rrow_lo != nullptr && c_ < p.N) ldg_nc_v8(rrow_lo + c_, l);
+          else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = __ldg(rp + j);
+            for (int j = 0; j < 8; ++j) l[j] = 0u;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      load_resid(0, rv_next);
+      if (do_resid) load_resid(0, rh[0], rl[0]);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(32 * q) << 16) + uint32_t(as * kBN + 128 * hf);
-#pragma unroll 1
-      for (int sc = 0; sc < 4; ++sc) {  // four 32-column slices; two slices = one 64-column TMA store
-        const int c_sc = col0 + 32 * sc;
-        uint4 rv[4];
+      const uint32_t t_row = tmem_base + (uint32_t(32 * q) << 16) + uint32_t(as * kBN + kEpiCols * cq);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rv[j] = rv_next[j];
-        if (sc < 3) load_resid(sc + 1, rv_next);
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(t_row + uint32_t(32 * sc), acc);
+      for (int piece = 0; piece < kEpiCols / kPiece; ++piece) {
+        const int c_p = col0 + kPiece * piece;
+        uint32_t acc[16];
+        tmem_ld_32x32b_x16(t_row + uint32_t(kPiece * piece), acc);
+        if (do_resid && piece + 1 < kEpiCols / kPiece) load_resid(piece + 1, rh[(piece + 1) & 1], rl[(piece + 1) & 1]);
         tmem_wait_ld();
-        if (sc == 3) {
+        if (piece == kEpiCols / kPiece - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA issuer
           tc_fence_before();
           __syncwarp();
@@ -366,13 +434,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             else mbar_arrive(tempty_bar(as));
           }
         }
-        if (p.out_f32 != nullptr) {
-          // split-K accumulation: add this partial slice straight from registers (16-byte vector reductions)
+        if (do_splitk) {
+          // split-K accumulation: add this partial piece straight from registers (16-byte vector reductions)
           if (row < p.M) {
-            float* dst = p.out_f32 + size_t(row) * p.N + c_sc;
+            float* dst = p.out_f32 + size_t(row) * p.N + c_p;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              if (c_sc + e < p.N)
+            for (int e = 0; e < kPiece; e += 4) {
+              if (c_p + e < p.N)
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + e), "f"(__uint_as_float(acc[e])),
                              "f"(__uint_as_float(acc[e + 1])), "f"(__uint_as_float(acc[e + 2])),
                              "f"(__uint_as_float(acc[e + 3])) : "memory");
@@ -380,73 +448,106 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           continue;
         }
-        if ((sc & 1) == 0 && store_pending) {
-          // staging buffer is about to be overwritten: previous TMA store must have read it
+        const uint32_t (&rhc)[8] = rh[piece & 1];
+        const uint32_t (&rlc)[8] = rl[piece & 1];
+        if ((piece & 1) == 0 && store_pending) {
+          // staging buffer is about to be overwritten: the previous TMA store(s) must have read it
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           store_pending = false;
         }
-        uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = reinterpret_cast<const float4*>(bias_s)[8 * sc + j];
-          const float4 c4 = reinterpret_cast<const float4*>(bias_s)[32 + 8 * sc + j];
-          // rstd*(acc - mean*colsum) + bias; without LN folding rstd = 1 and colsum = 0: plain acc + bias
-          uint64_t v01 = fma_f32x2(pack_f32x2(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1])), ln_rstd2,
-                                   fma_f32x2(ln_nmr2, pack_f32x2(c4.x, c4.y), pack_f32x2(b4.x, b4.y)));
-          uint64_t v23 = fma_f32x2(pack_f32x2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])), ln_rstd2,
-                                   fma_f32x2(ln_nmr2, pack_f32x2(c4.z, c4.w), pack_f32x2(b4.z, b4.w)));
-          if (p.act == 1) {
-            v01 = gelu_erf_x2(v01);
-            v23 = gelu_erf_x2(v23);
-          }
-          const uint32_t r01 = (j & 1) ? rv[j >> 1].z : rv[j >> 1].x;  // columns 4j, 4j+1
-          const uint32_t r23 = (j & 1) ? rv[j >> 1].w : rv[j >> 1].y;  // columns 4j+2, 4j+3
-          if (p.act == 2) {
-            // backward of fc1's GELU: the "residual" operand holds the saved pre-activation u; y = acc * gelu'(u)
-            v01 = mul_f32x2(v01, pack_f32x2(gelu_erf_grad(bf16_lo(r01)), gelu_erf_grad(bf16_hi(r01))));
-            v23 = mul_f32x2(v23, pack_f32x2(gelu_erf_grad(bf16_lo(r23)), gelu_erf_grad(bf16_hi(r23))));
-          } else {
-            v01 = add_f32x2(v01, pack_f32x2(bf16_lo(r01), bf16_hi(r01)));
-            v23 = add_f32x2(v23, pack_f32x2(bf16_lo(r23), bf16_hi(r23)));
-          }
-          if (p.out_row_sums != nullptr) {
-            // LayerNorm statistics of the NEXT layer's input, gathered while the row is in registers (fp32 values
-            // before the bf16 rounding: the difference is O(2^-9/sqrt(d)) on the mean)
-            rs2 = add_f32x2(rs2, add_f32x2(v01, v23));
-            rss2 = fma_f32x2(v01, v01, fma_f32x2(v23, v23, rss2));
-          }
-          float v0, v1, v2, v3;
-          unpack_f32x2(v01, v0, v1);
-          unpack_f32x2(v23, v2, v3);
-          packed[2 * j + 0] = pack_bf16x2(v0, v1);
-          packed[2 * j + 1] = pack_bf16x2(v2, v3);
-        }
-        // swizzled (128B pattern) store into the staging tile: row = lane, 16B chunk index ^ (row & 7)
+        for (int j = 0; j < 2; ++j) {       // one 16-byte staging chunk (8 columns) per step
+          uint32_t hp[4], lp[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = (sc & 1) * 4 + j;
-          const uint32_t addr = stg + uint32_t(lane * 128) + uint32_t(((chunk ^ (lane & 7)) << 4));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * j + 0]),
-                       "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
-                       : "memory");
+          for (int ii = 0; ii < 2; ++ii) {   // four columns per step
+            const int i = 2 * j + ii;
+            const float4 b4 = bias_s4[4 * piece + i];
+            uint64_t v01 = pack_f32x2(__uint_as_float(acc[4 * i + 0]), __uint_as_float(acc[4 * i + 1]));
+            uint64_t v23 = pack_f32x2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3]));
+            if (do_ln) {
+              // rstd*(acc - mean*colsum) + bias
+              const float4 c4 = bias_s4[16 + 4 * piece + i];
+              v01 = fma_f32x2(v01, ln_rstd2, fma_f32x2(ln_nmr2, pack_f32x2(c4.x, c4.y), pack_f32x2(b4.x, b4.y)));
+              v23 = fma_f32x2(v23, ln_rstd2, fma_f32x2(ln_nmr2, pack_f32x2(c4.z, c4.w), pack_f32x2(b4.z, b4.w)));
+            } else {
+              v01 = add_f32x2(v01, pack_f32x2(b4.x, b4.y));
+              v23 = add_f32x2(v23, pack_f32x2(b4.z, b4.w));
+            }
+            if (do_gelu) {
+              v01 = gelu_erf_x2(v01);
+              v23 = gelu_erf_x2(v23);
+            }
+            if (do_act2) {
+              // backward of fc1's GELU: the "residual" operand holds the saved pre-activation u; y = acc * gelu'(u)
+              const uint32_t r01 = rhc[2 * i], r23 = rhc[2 * i + 1];
+              v01 = mul_f32x2(v01, pack_f32x2(gelu_erf_grad(bf16_lo(r01)), gelu_erf_grad(bf16_hi(r01))));
+              v23 = mul_f32x2(v23, pack_f32x2(gelu_erf_grad(bf16_lo(r23)), gelu_erf_grad(bf16_hi(r23))));
+            } else if (do_resid) {
+              v01 = add_f32x2(v01, bf16x2_to_f32x2(rhc[2 * i]));
+              v23 = add_f32x2(v23, bf16x2_to_f32x2(rhc[2 * i + 1]));
+              if constexpr (kHiLo) {
+                v01 = add_f32x2(add_f32x2(v01, bf16x2_to_f32x2(rlc[2 * i])), roff2);
+                v23 = add_f32x2(add_f32x2(v23, bf16x2_to_f32x2(rlc[2 * i + 1])), roff2);
+              }
+            }
+            if (do_sums) {
+              // LayerNorm statistics of the NEXT layer's input, gathered while the row is in registers (fp32 values
+              // before any rounding), as sums of (v - shift) with shift = the row's first value of this 64-column slice
+              if (piece == 0 && i == 0) {
+                float v0_, v1_;
+                unpack_f32x2(v01, v0_, v1_);
+                shift = v0_;
+                nshift2 = pack_f32x2(-shift, -shift);
+              }
+              const uint64_t d01 = add_f32x2(v01, nshift2), d23 = add_f32x2(v23, nshift2);
+              s1 = add_f32x2(s1, add_f32x2(d01, d23));
+              s2 = fma_f32x2(d01, d01, fma_f32x2(d23, d23, s2));
+            }
+            float v0, v1, v2, v3;
+            unpack_f32x2(v01, v0, v1);
+            unpack_f32x2(v23, v2, v3);
+            const uint32_t h01 = pack_bf16x2(v0, v1), h23 = pack_bf16x2(v2, v3);
+            hp[2 * ii + 0] = h01;
+            hp[2 * ii + 1] = h23;
+            if constexpr (kHiLo) {
+              // low half of the split representation: bf16(v - float(hi)); hi + lo carries 16 mantissa bits
+              float l0, l1, l2, l3;
+              unpack_f32x2(add_f32x2(v01, pack_f32x2(-bf16_lo(h01), -bf16_hi(h01))), l0, l1);
+              unpack_f32x2(add_f32x2(v23, pack_f32x2(-bf16_lo(h23), -bf16_hi(h23))), l2, l3);
+              lp[2 * ii + 0] = pack_bf16x2(l0, l1);
+              lp[2 * ii + 1] = pack_bf16x2(l2, l3);
+            }
+          }
+          // 64B-swizzled store into the staging tile(s): row = lane, 32 bytes of this piece = chunks 2*(piece&1), +1
+          const uint32_t chunk = uint32_t((piece & 1) * 2 + j);
+          const uint32_t addr = srow + ((chunk ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]),
+                       "r"(hp[3]) : "memory");
+          if constexpr (kHiLo) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048u), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]),
+                         "r"(lp[3]) : "memory");
+          }
         }
-        if (sc & 1) {
+        if (piece & 1) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && (c_sc - 32) < p.N) {
-            tma_store_2d(&tm_y, stg, c_sc - 32, row0);
+          if (lane == 0 && row0 < p.M && (c_p - kPiece) < p.N) {
+            tma_store_2d(&tm_y, stg, c_p - kPiece, row0);
+            if constexpr (kHiLo) {
+              if (p.has_out_lo) tma_store_2d(&tm_ylo, stg + 2048u, c_p - kPiece, row0);
+            }
             tma_store_commit();
           }
           store_pending = true;
         }
       }
-      if (p.out_row_sums != nullptr && row < p.M) {
+      if (do_sums && row < p.M && col0 < p.N) {
         float a0, a1, q0, q1;
-        unpack_f32x2(rs2, a0, a1);
-        unpack_f32x2(rss2, q0, q1);
-        float2* dst = reinterpret_cast<float2*>(p.out_row_sums) + size_t(row) * (2 * p.num_n_tiles) + (2 * n_tile + hf);
-        *dst = make_float2(a0 + a1, q0 + q1);
+        unpack_f32x2(s1, a0, a1);
+        unpack_f32x2(s2, q0, q1);
+        float4* dst = reinterpret_cast<float4*>(p.out_row_sums) + size_t(row) * ((p.N + 63) >> 6) + (col0 >> 6);
+        *dst = make_float4(shift, a0 + a1, q0 + q1, 0.f);
       }
       if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
@@ -459,81 +560,92 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) tmem_dealloc<CG>(tmem_base, kTmemCols);
+  timeline_end(p.tl);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int CG>
-static int launch_gemm(const void* x, const void* w, const float* bias, const void* resid, int ldr, void* y, int M,
-                       int N, int K, int act, const float* row_stats, const float* colsum, int ln_sums, float ln_eps,
-                       float* out_row_sums, cudaStream_t stream, float* out_f32 = nullptr, int split_k = 1,
-                       int resid_period = 0, int mn_major = 0) {
-  using Cfg = GemmCfg<CG>;
-  CUtensorMap tm_a, tm_b, tm_y;
-  if (mn_major) {
+struct GemmCall {
+  const void* x; const void* w; const float* bias;
+  const void* resid; const void* resid_lo; int ldr;
+  void* y; void* y_lo;
+  int M, N, K, act;
+  const float* row_stats; const float* colsum; int ln_sums; float ln_eps;
+  float* out_row_sums;
+  float* out_f32; int split_k; int resid_period; int mn_major;
+  const float* row_offset;
+};
+
+template <int CG, int MODE>
+static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
+  constexpr bool kHiLo = (MODE == kEpiRes);
+  using Cfg = GemmCfg<CG, kHiLo>;
+  const int M = c.M, N = c.N, K = c.K;
+  CUtensorMap tm_a, tm_b, tm_y, tm_ylo;
+  if (c.mn_major) {
     // x = dY [K tokens, M], w = X [K tokens, N], both row-major: 64 x 64 boxes with the output dimension innermost
     uint32_t box[2] = {64u, uint32_t(kBK)};
     uint64_t dims_a[2] = {uint64_t(M), uint64_t(K)};
     uint64_t str_a[1] = {uint64_t(M) * 2};
-    int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims_a, str_a, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.x, dims_a, str_a, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     uint64_t dims_b[2] = {uint64_t(N), uint64_t(K)};
     uint64_t str_b[1] = {uint64_t(N) * 2};
-    rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims_b, str_b, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w, dims_b, str_b, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   } else {
     {
       uint64_t dims[2] = {uint64_t(K), uint64_t(M)};
       uint64_t strides[1] = {uint64_t(K) * 2};
       uint32_t box[2] = {uint32_t(kBK), uint32_t(kBM)};
-      int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
     {
       uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
       uint64_t strides[1] = {uint64_t(K) * 2};
       uint32_t box[2] = {uint32_t(kBK), uint32_t(Cfg::kBRows)};
-      int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
   }
   {
-    // (in split-K mode the bf16 output map is unused; it is encoded over the X operand only to keep the launch uniform)
-    const uint64_t inner = out_f32 ? uint64_t(mn_major ? M : K) : uint64_t(N);
-    const uint64_t outer = out_f32 ? uint64_t(mn_major ? K : M) : uint64_t(M);
+    // output tiles leave as 32-row x 32-column boxes (64-byte rows, 64B swizzle).  In split-K mode the bf16 output map is
+    // unused; it is encoded over the X operand only to keep the launch uniform.
+    const uint64_t inner = c.out_f32 ? uint64_t(c.mn_major ? M : K) : uint64_t(N);
+    const uint64_t outer = c.out_f32 ? uint64_t(c.mn_major ? K : M) : uint64_t(M);
     uint64_t dims[2] = {inner, outer};
     uint64_t strides[1] = {inner * 2};
-    uint32_t box[2] = {64u, 32u};
-    int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_f32 ? x : y, dims, strides, box,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
+    uint32_t box[2] = {32u, 32u};
+    int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.out_f32 ? c.x : c.y, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    rc = encode_tmap(&tm_ylo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.out_f32 ? c.x : (c.y_lo ? c.y_lo : c.y), dims, strides,
+                     box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   }
   GemmParams p;
-  p.bias = bias;
-  p.resid = reinterpret_cast<const __nv_bfloat16*>(resid);
-  p.ldr = ldr;
-  p.resid_period = resid_period;
-  {
-    static int ld256 = -1;   // MT_B200_RESID256=0 falls back to 16-byte loads (A/B runs)
-    if (ld256 < 0) {
-      const char* e = getenv("MT_B200_RESID256");
-      ld256 = (e && e[0] == '0') ? 0 : 1;
-    }
-    p.resid_ld256 = (ld256 && resid != nullptr && (reinterpret_cast<uintptr_t>(resid) & 31) == 0 && (ldr % 16) == 0) ? 1 : 0;
-  }
-  p.mn_major = mn_major;
+  p.bias = c.bias;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(c.resid);
+  p.resid_lo = reinterpret_cast<const __nv_bfloat16*>(c.resid_lo);
+  p.ldr = c.ldr;
+  p.resid_period = c.resid_period;
+  p.mn_major = c.mn_major;
   p.M = M; p.N = N; p.K = K;
-  p.act = act;
-  p.row_stats = reinterpret_cast<const float2*>(row_stats);
-  p.colsum = colsum;
-  p.ln_sums = ln_sums;
-  p.ln_eps = ln_eps;
-  p.out_row_sums = out_row_sums;
-  p.out_f32 = out_f32;
+  p.act = c.act;
+  p.row_stats = c.row_stats;
+  p.colsum = c.colsum;
+  p.ln_sums = c.ln_sums;
+  p.ln_eps = c.ln_eps;
+  p.out_row_sums = c.out_row_sums;
+  p.has_out_lo = c.y_lo != nullptr ? 1 : 0;
+  p.row_offset = c.row_offset;
+  p.out_f32 = c.out_f32;
+  p.tl = timeline_next_slot();
   {
     const int num_kb = ceil_div(K, kBK);
-    int sk = split_k < 1 ? 1 : (split_k > num_kb ? num_kb : split_k);
+    int sk = c.split_k < 1 ? 1 : (c.split_k > num_kb ? num_kb : c.split_k);
     p.kb_per_split = ceil_div(num_kb, sk);
     p.split_k = ceil_div(num_kb, p.kb_per_split);   // every split non-empty
   }
@@ -548,7 +660,7 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
 
-  auto kern = gemm_bf16_kernel<CG>;
+  auto kern = gemm_bf16_kernel<CG, MODE>;
   {
     // the opt-in to > 48 KB of dynamic shared memory is per device (nn.DataParallel drives several from one process)
     static bool attr_set[64] = {false};
@@ -560,16 +672,26 @@ static int launch_gemm(const void* x, const void* w, const float* bias, const vo
     }
   }
   MT_CHECK_CUDA(launch_pdl(kern, dim3(unsigned(clusters * CG), 1, 1), dim3(kGemmThreads, 1, 1), size_t(Cfg::kSmemBytes),
-                           stream, unsigned(CG), tm_a, tm_b, tm_y, p));
+                           stream, unsigned(CG), tm_a, tm_b, tm_y, tm_ylo, p));
   return MT_OK;
+}
+
+// picks the epilogue specialisation for a call
+template <int CG>
+static int dispatch_gemm(const GemmCall& c, cudaStream_t s) {
+  const bool special_ok = c.out_f32 == nullptr && c.act != 2 && c.resid_period == 0 && !c.mn_major;
+  if (special_ok && c.row_stats != nullptr && c.resid == nullptr && c.out_row_sums == nullptr && c.y_lo == nullptr) {
+    if (c.act == 1) return launch_gemm<CG, kEpiLnGelu>(c, s);
+    return launch_gemm<CG, kEpiLn>(c, s);
+  }
+  if (special_ok && c.resid != nullptr && c.act == 0 && c.row_stats == nullptr) return launch_gemm<CG, kEpiRes>(c, s);
+  return launch_gemm<CG, kEpiGeneric>(c, s);
 }
 
 }  // namespace mt
 
-static int gemm_entry(const char* who, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                      int M, int N, int K, int act, const float* row_stats, const float* colsum, int cta_group,
-                      void* stream, int ln_sums = 0, float ln_eps = 0.f, float* out_row_sums = nullptr,
-                      int resid_period = 0) {
+static int gemm_entry(const char* who, const void* x, const void* w, void* y, int M, int N, int K, const mt_gemm_opts& o,
+                      void* stream) {
   using namespace mt;
   MT_REQUIRE(x && w && y, MT_ERR_BAD_SHAPE, "%s: null pointer", who);
   MT_REQUIRE(M > 0 && N > 0 && K > 0, MT_ERR_BAD_SHAPE, "%s: M,N,K must be positive (got %d,%d,%d)", who, M, N, K);
@@ -577,18 +699,32 @@ static int gemm_entry(const char* who, const void* x, const void* w, const float
              "%s: K and N must be multiples of 8 (16-byte rows for TMA); got K=%d N=%d", who, K, N);
   MT_REQUIRE(N % 32 == 0, MT_ERR_BAD_SHAPE, "%s: N must be a multiple of 32 (got %d)", who, N);
   MT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(colsum) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(row_stats) & 7) == 0,
+                 (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(o.y_lo) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(o.bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(o.ln_colsum) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(o.ln_row_stats) & 7) == 0,
              MT_ERR_BAD_ALIGN, "%s: all pointers must be 16-byte aligned", who);
-  MT_REQUIRE(act == 0 || act == 1 || act == 2, MT_ERR_UNSUPPORTED,
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(o.residual) & 31) == 0 && (reinterpret_cast<uintptr_t>(o.residual_lo) & 31) == 0,
+             MT_ERR_BAD_ALIGN, "%s: residual pointers must be 32-byte aligned (rows are read as whole 32-byte sectors)", who);
+  MT_REQUIRE(o.act == 0 || o.act == 1 || o.act == 2, MT_ERR_UNSUPPORTED,
              "%s: act must be 0 (none), 1 (gelu) or 2 (times gelu'(residual))", who);
-  MT_REQUIRE(act != 2 || residual != nullptr, MT_ERR_BAD_SHAPE, "%s: act 2 needs the pre-activation as `residual`", who);
-  MT_REQUIRE(resid_period >= 0 && (resid_period == 0 || (residual != nullptr && act != 2)), MT_ERR_BAD_SHAPE,
+  MT_REQUIRE(o.act != 2 || o.residual != nullptr, MT_ERR_BAD_SHAPE, "%s: act 2 needs the pre-activation as `residual`", who);
+  MT_REQUIRE(o.residual_period >= 0 && (o.residual_period == 0 || (o.residual != nullptr && o.act != 2)), MT_ERR_BAD_SHAPE,
              "%s: residual_period needs a residual table and act != 2", who);
-  MT_REQUIRE((row_stats == nullptr) == (colsum == nullptr), MT_ERR_BAD_SHAPE,
+  MT_REQUIRE((o.ln_row_stats == nullptr) == (o.ln_colsum == nullptr), MT_ERR_BAD_SHAPE,
              "%s: row_stats and colsum must be given together", who);
+  MT_REQUIRE(o.ln_stats_are_sums == 0 || o.ln_stats_are_sums == (K + 63) / 64, MT_ERR_BAD_SHAPE,
+             "%s: ln_stats_are_sums must be 0 or ceil(K/64) = %d (got %d)", who, (K + 63) / 64, o.ln_stats_are_sums);
+  MT_REQUIRE(o.ln_stats_are_sums == 0 || (reinterpret_cast<uintptr_t>(o.ln_row_stats) & 15) == 0, MT_ERR_BAD_ALIGN,
+             "%s: partial-sum statistics must be 16-byte aligned", who);
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(o.out_row_sums) & 15) == 0, MT_ERR_BAD_ALIGN,
+             "%s: out_row_sums must be 16-byte aligned", who);
+  // the split (hi + lo) residual stream exists in the residual epilogue only
+  const bool split_ok = o.residual != nullptr && o.act == 0 && o.ln_row_stats == nullptr && o.residual_period == 0;
+  MT_REQUIRE((o.residual_lo == nullptr && o.y_lo == nullptr && o.y_row_offset == nullptr) || split_ok, MT_ERR_UNSUPPORTED,
+             "%s: residual_lo / y_lo / y_row_offset need a plain residual GEMM (residual given, act 0, no LayerNorm fold, "
+             "no period)", who);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int cta_group = o.cta_group;
   if (cta_group == 0) {
     // auto: CTA pairs unless overridden (MT_B200_GEMM_CG=1|2, read once; for A/B experiments only)
     static int auto_cg = 0;
@@ -598,20 +734,23 @@ static int gemm_entry(const char* who, const void* x, const void* w, const float
     }
     cta_group = auto_cg;
   }
-  MT_REQUIRE((reinterpret_cast<uintptr_t>(out_row_sums) & 7) == 0, MT_ERR_BAD_ALIGN, "%s: out_row_sums must be 8-byte aligned", who);
-  if (cta_group == 1)
-    return launch_gemm<1>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s,
-                          nullptr, 1, resid_period);
-  if (cta_group == 2)
-    return launch_gemm<2>(x, w, bias, residual, N, y, M, N, K, act, row_stats, colsum, ln_sums, ln_eps, out_row_sums, s,
-                          nullptr, 1, resid_period);
+  GemmCall c = {};
+  c.x = x; c.w = w; c.bias = o.bias; c.resid = o.residual; c.resid_lo = o.residual_lo; c.ldr = N;
+  c.y = y; c.y_lo = o.y_lo; c.M = M; c.N = N; c.K = K; c.act = o.act;
+  c.row_stats = o.ln_row_stats; c.colsum = o.ln_colsum; c.ln_sums = o.ln_stats_are_sums; c.ln_eps = o.ln_eps;
+  c.row_offset = o.y_row_offset;
+  c.out_row_sums = o.out_row_sums; c.out_f32 = nullptr; c.split_k = 1; c.resid_period = o.residual_period; c.mn_major = 0;
+  if (cta_group == 1) return dispatch_gemm<1>(c, s);
+  if (cta_group == 2) return dispatch_gemm<2>(c, s);
   set_error("%s: cta_group must be 0 (auto), 1 or 2", who);
   return MT_ERR_UNSUPPORTED;
 }
 
 extern "C" int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* residual, void* y, int M,
                             int N, int K, int act, int cta_group, void* stream) {
-  return gemm_entry("mt_gemm_bf16", x, w, bias, residual, y, M, N, K, act, nullptr, nullptr, cta_group, stream);
+  mt_gemm_opts o = {};
+  o.bias = bias; o.residual = residual; o.act = act; o.cta_group = cta_group;
+  return gemm_entry("mt_gemm_bf16", x, w, y, M, N, K, o, stream);
 }
 
 extern "C" int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float* bias_folded, const float* colsum,
@@ -621,8 +760,9 @@ extern "C" int mt_gemm_bf16_ln(const void* x, const void* w_folded, const float*
     mt::set_error("mt_gemm_bf16_ln: row_stats and colsum are required");
     return MT_ERR_BAD_SHAPE;
   }
-  return gemm_entry("mt_gemm_bf16_ln", x, w_folded, bias_folded, nullptr, y, M, N, K, act, row_stats, colsum, cta_group,
-                    stream);
+  mt_gemm_opts o = {};
+  o.bias = bias_folded; o.act = act; o.ln_colsum = colsum; o.ln_row_stats = row_stats; o.cta_group = cta_group;
+  return gemm_entry("mt_gemm_bf16_ln", x, w_folded, y, M, N, K, o, stream);
 }
 
 extern "C" int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int N, int K, const mt_gemm_opts* o,
@@ -631,8 +771,7 @@ extern "C" int mt_gemm_bf16_ex(const void* x, const void* w, void* y, int M, int
     mt::set_error("mt_gemm_bf16_ex: opts is required");
     return MT_ERR_BAD_SHAPE;
   }
-  return gemm_entry("mt_gemm_bf16_ex", x, w, o->bias, o->residual, y, M, N, K, o->act, o->ln_row_stats, o->ln_colsum,
-                    o->cta_group, stream, o->ln_stats_are_sums, o->ln_eps, o->out_row_sums, o->residual_period);
+  return gemm_entry("mt_gemm_bf16_ex", x, w, y, M, N, K, *o, stream);
 }
 
 // Number of K splits for the fp32-accumulating (weight-gradient) GEMM: (output tiles x splits) should fill whole waves of
@@ -673,7 +812,9 @@ extern "C" int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, i
     splits = auto_splits(ceil_div(M, 2 * kBM) * ceil_div(N, kBN), ceil_div(K, kBK), sms);
   }
   MT_CHECK_CUDA(cudaMemsetAsync(y_f32, 0, size_t(M) * N * sizeof(float), s));
-  return launch_gemm<2>(x, w, nullptr, nullptr, N, nullptr, M, N, K, 0, nullptr, nullptr, 0, 0.f, nullptr, s, y_f32, splits);
+  GemmCall c = {};
+  c.x = x; c.w = w; c.ldr = N; c.M = M; c.N = N; c.K = K; c.out_f32 = y_f32; c.split_k = splits;
+  return launch_gemm<2, kEpiGeneric>(c, s);
 }
 
 // dW_f32[N_out, K_in] = dY[T, N_out]^T @ X[T, K_in]: the weight gradient read straight from the two row-major activation
@@ -694,6 +835,7 @@ extern "C" int mt_gemm_bf16_wgrad(const void* dy, const void* x, float* dw_f32, 
     splits = auto_splits(ceil_div(N_out, 2 * kBM) * ceil_div(K_in, kBN), ceil_div(T, kBK), sms);
   }
   MT_CHECK_CUDA(cudaMemsetAsync(dw_f32, 0, size_t(N_out) * K_in * sizeof(float), s));
-  return launch_gemm<2>(dy, x, nullptr, nullptr, K_in, nullptr, N_out, K_in, T, 0, nullptr, nullptr, 0, 0.f, nullptr, s,
-                        dw_f32, splits, 0, 1);
+  GemmCall c = {};
+  c.x = dy; c.w = x; c.ldr = K_in; c.M = N_out; c.N = K_in; c.K = T; c.out_f32 = dw_f32; c.split_k = splits; c.mn_major = 1;
+  return launch_gemm<2, kEpiGeneric>(c, s);
 }

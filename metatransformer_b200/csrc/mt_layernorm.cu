@@ -113,12 +113,14 @@ layernorm_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma, con
 // makes the normalised activations never touch HBM.  Algorithmic traffic: M*d*sizeof(in) + 8*M bytes.
 template <int NV, typename TIn>
 __global__ void __launch_bounds__(kLnWarps * 32)
-row_stats_kernel(const TIn* __restrict__ x, float2* __restrict__ stats, int M, int d, float eps) {
+row_stats_kernel(const TIn* __restrict__ x, float2* __restrict__ stats, int M, int d, float eps,
+                 unsigned long long* tl) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + warp;
   pdl_launch_dependents();
   pdl_wait();
-  if (row >= M) return;
+  timeline_start(tl);
+  if (row >= M) { timeline_end(tl); return; }
   const TIn* xr = x + size_t(row) * d;
   const float inv_d = 1.0f / float(d);
   float mean, q = 0.f;
@@ -156,6 +158,91 @@ row_stats_kernel(const TIn* __restrict__ x, float2* __restrict__ stats, int M, i
   }
   const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
   if (lane == 0) stats[row] = make_float2(mean, rstd);
+  __syncthreads();
+  timeline_end(tl);
+}
+
+// Entry of the whole-encoder driver: per row  c = mean(x),  xc = x - c  ->  split pair hi = bf16(xc), lo = bf16(xc - hi),
+// plus the LayerNorm statistics of the CENTRED row (mean 0, rstd).  LayerNorm is shift-invariant and the residual adds
+// commute with a per-row constant, so the whole Block stack runs on the centred stream unchanged and c is added back in
+// the last epilogue.  Why: the LN-folded GEMMs consume bf16(x) instead of bf16(LN(x)), whose rounding error scales with
+// |x| instead of |x - mean|; centring removes the row offset before anything is rounded (rows with |mean| >> std).
+// One warp per row, 16-byte loads / 8-byte-pair stores; traffic = M*d*(sizeof(in) + 4) bytes.
+template <typename TIn>
+__global__ void __launch_bounds__(kLnWarps * 32)
+center_split_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                    float* __restrict__ c_row, float2* __restrict__ stats, int M, int d, float eps, unsigned long long* tl) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + warp;
+  timeline_start(tl);
+  if (row < M) {
+    const TIn* xr = x + size_t(row) * d;
+    const float inv_d = 1.0f / float(d);
+    const int nchunks = d >> 3;
+    float s = 0.f;
+    for (int c = lane; c < nchunks; c += 32) {
+      float v[8];
+      load8<TIn>(xr + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+    for (int c = lane; c < nchunks; c += 32) {   // second pass hits L1 (row <= 16 KB)
+      float v[8];
+      load8<TIn>(xr + c * 8, v);
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float a = v[j] - mean, b = v[j + 1] - mean;
+        q = fmaf(a, a, fmaf(b, b, q));
+        const uint32_t hh = pack_bf16x2(a, b);
+        h[j >> 1] = hh;
+        l[j >> 1] = pack_bf16x2(a - bf16_lo(hh), b - bf16_hi(hh));
+      }
+      *reinterpret_cast<uint4*>(hi + size_t(row) * d + c * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(lo + size_t(row) * d + c * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+    if (lane == 0) {
+      c_row[row] = mean;
+      stats[row] = make_float2(0.f, rstd);
+    }
+  }
+  __syncthreads();
+  timeline_end(tl);
+}
+
+// same for a split (hi + lo) row: the statistics of hi + lo (residual stream of the per-Block path)
+__global__ void __launch_bounds__(kLnWarps * 32)
+row_stats_split_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, float2* __restrict__ stats,
+                       int M, int d, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + warp;
+  if (row >= M) return;
+  const __nv_bfloat16* hr = xh + size_t(row) * d;
+  const __nv_bfloat16* lr = xl + size_t(row) * d;
+  const float inv_d = 1.0f / float(d);
+  const int nchunks = d >> 3;
+  float s = 0.f;
+  for (int c = lane; c < nchunks; c += 32) {
+    float v[8], w[8];
+    load8<__nv_bfloat16>(hr + c * 8, v);
+    load8<__nv_bfloat16>(lr + c * 8, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j] + w[j];
+  }
+  const float mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+  for (int c = lane; c < nchunks; c += 32) {   // second pass hits L1 (row <= 16 KB)
+    float v[8], w[8];
+    load8<__nv_bfloat16>(hr + c * 8, v);
+    load8<__nv_bfloat16>(lr + c * 8, w);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float t = (v[j] - mean) + w[j]; q = fmaf(t, t, q); }
+  }
+  const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
 }
 
 template <typename TIn>
@@ -164,9 +251,10 @@ static int launch_row_stats(const void* x, float* stats, int M, int d, float eps
   float2* sp = reinterpret_cast<float2*>(stats);
   const unsigned grid = unsigned(ceil_div(M, kLnWarps));
   const unsigned block = kLnWarps * 32;
-  if (d == 768) MT_CHECK_CUDA(launch_pdl(row_stats_kernel<3, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps));
-  else if (d == 1024) MT_CHECK_CUDA(launch_pdl(row_stats_kernel<4, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps));
-  else MT_CHECK_CUDA(launch_pdl(row_stats_kernel<0, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps));
+  unsigned long long* tl = timeline_next_slot();
+  if (d == 768) MT_CHECK_CUDA(launch_pdl(row_stats_kernel<3, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps, tl));
+  else if (d == 1024) MT_CHECK_CUDA(launch_pdl(row_stats_kernel<4, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps, tl));
+  else MT_CHECK_CUDA(launch_pdl(row_stats_kernel<0, TIn>, dim3(grid), dim3(block), 0, s, 1u, xp, sp, M, d, eps, tl));
   return MT_OK;
 }
 
@@ -241,6 +329,47 @@ extern "C" int mt_row_stats(const void* x, int x_dtype, float* stats, int M, int
   if (x_dtype == MT_DT_F32) return launch_row_stats<float>(x, stats, M, d, eps, s);
   set_error("mt_row_stats: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
   return MT_ERR_BAD_DTYPE;
+}
+
+extern "C" int mt_center_split(const void* x, int x_dtype, void* hi, void* lo, float* c_row, float* stats, int M, int d,
+                               float eps, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x && hi && lo && c_row && stats, MT_ERR_BAD_SHAPE, "mt_center_split: null pointer");
+  MT_REQUIRE(M > 0 && d > 0 && d % 8 == 0, MT_ERR_BAD_SHAPE, "mt_center_split: need M > 0 and d %% 8 == 0 (M=%d d=%d)", M, d);
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(stats) & 7) == 0 && (reinterpret_cast<uintptr_t>(c_row) & 3) == 0,
+             MT_ERR_BAD_ALIGN, "mt_center_split: x / hi / lo must be 16-byte, stats 8-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = unsigned(ceil_div(M, kLnWarps));
+  unsigned long long* tl = timeline_next_slot();
+  __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(hi);
+  __nv_bfloat16* lp = reinterpret_cast<__nv_bfloat16*>(lo);
+  float2* sp = reinterpret_cast<float2*>(stats);
+  if (x_dtype == MT_DT_BF16)
+    center_split_kernel<__nv_bfloat16><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), hp, lp, c_row,
+                                                                      sp, M, d, eps, tl);
+  else if (x_dtype == MT_DT_F32)
+    center_split_kernel<float><<<grid, kLnWarps * 32, 0, s>>>(reinterpret_cast<const float*>(x), hp, lp, c_row, sp, M, d, eps, tl);
+  else {
+    set_error("mt_center_split: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
+    return MT_ERR_BAD_DTYPE;
+  }
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+extern "C" int mt_row_stats_split(const void* x_hi, const void* x_lo, float* stats, int M, int d, float eps, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(x_hi && x_lo && stats, MT_ERR_BAD_SHAPE, "mt_row_stats_split: null pointer");
+  MT_REQUIRE(M > 0 && d > 0 && d % 8 == 0, MT_ERR_BAD_SHAPE, "mt_row_stats_split: need M > 0 and d %% 8 == 0 (M=%d d=%d)", M, d);
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(x_hi) | reinterpret_cast<uintptr_t>(x_lo)) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+             MT_ERR_BAD_ALIGN, "mt_row_stats_split: x must be 16-byte and stats 8-byte aligned");
+  row_stats_split_kernel<<<unsigned(ceil_div(M, kLnWarps)), kLnWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_hi), reinterpret_cast<const __nv_bfloat16*>(x_lo),
+      reinterpret_cast<float2*>(stats), M, d, eps);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
 }
 
 extern "C" int mt_fold_layernorm(const void* w, int w_dtype, const float* gamma, const float* beta, const float* bias,

@@ -339,6 +339,19 @@ MT_DEVINL uint64_t add_f32x2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// device timeline (mt_timeline_begin): slot[0] = earliest CTA start, slot[1] = latest CTA end, in %globaltimer ns
+MT_DEVINL unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+MT_DEVINL void timeline_start(unsigned long long* tl) {
+  if (tl != nullptr && threadIdx.x == 0) atomicMin(tl, globaltimer_ns());
+}
+MT_DEVINL void timeline_end(unsigned long long* tl) {
+  if (tl != nullptr && threadIdx.x == 0) atomicMax(tl + 1, globaltimer_ns());
+}
+
 MT_DEVINL void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -135,8 +135,19 @@ class FusedEncoder(nn.Module):
         if C != self.dim:
             raise ValueError(f"FusedEncoder: expected last dim {self.dim}, got {C}")
         xin = x.contiguous()
-        xb = xin if xin.dtype == torch.bfloat16 else ops.cast(xin, torch.bfloat16)
-        y = out if (out is not None and out.dtype == torch.bfloat16) else torch.empty_like(xb)
+        if xin.dtype not in (torch.bfloat16, torch.float32):
+            xin = ops.cast(xin, torch.bfloat16)          # fp16 callers: bf16 has the range, the stream is split inside
+        io_dt = xin.dtype                                  # bf16 or fp32, handed to the driver as is
+        if out is not None:
+            if out.dtype != io_dt or tuple(out.shape) != tuple(xin.shape) or out.device != xin.device \
+                    or not out.is_contiguous():
+                raise ValueError(f"FusedEncoder: out must be a contiguous {io_dt} tensor of shape {tuple(xin.shape)} on "
+                                 f"{xin.device} (got {out.dtype}, {tuple(out.shape)}, {out.device})")
+            y = out
+        else:
+            y = torch.empty_like(xin)
+        xb = xin
+        dt_code = _lib.MT_DT_BF16 if io_dt == torch.bfloat16 else _lib.MT_DT_F32
         need = ctypes.c_size_t()
         check(lib.mt_encoder_workspace_bytes(self._handle, B, N, ctypes.byref(need)), "mt_encoder_workspace_bytes")
         if self._ws is None or self._ws.numel() < need.value or self._ws.device != x.device:
@@ -144,14 +155,15 @@ class FusedEncoder(nn.Module):
             self._graphs.clear()
 
         def launch():
-            check(lib.mt_encoder_forward(self._handle, xb.data_ptr(), y.data_ptr(), B, N, self._ws.data_ptr(),
-                                         self._ws.numel(), torch.cuda.current_stream().cuda_stream), "mt_encoder_forward")
+            check(lib.mt_encoder_forward_ex(self._handle, xb.data_ptr(), dt_code, y.data_ptr(), dt_code, B, N,
+                                            self._ws.data_ptr(), self._ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream), "mt_encoder_forward_ex")
 
         with torch.cuda.device(x.device):
-            if not self.use_cuda_graph:
+            if not self.use_cuda_graph or xb is not x:       # a per-call staging copy would be re-captured every call
                 launch()
             else:
-                key = (xb.data_ptr(), y.data_ptr(), B, N, self._handle_key)
+                key = (xb.data_ptr(), y.data_ptr(), B, N, io_dt, self._handle_key)
                 g = self._graphs.get(key)
                 if g is None:
                     launch()                         # warm-up outside capture (function attributes, lazy module load)
@@ -163,6 +175,4 @@ class FusedEncoder(nn.Module):
                         self._graphs.clear()
                     self._graphs[key] = g
                 g.replay()
-        if x.dtype == torch.bfloat16:
-            return y
-        return ops.cast(y, x.dtype)
+        return y if y.dtype == x.dtype else ops.cast(y, x.dtype)

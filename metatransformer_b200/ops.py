@@ -51,28 +51,35 @@ def cast(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, gelu: bool = False, cta_group: int = 0,
-           out: Optional[torch.Tensor] = None, residual_period: int = 0) -> torch.Tensor:
+           out: Optional[torch.Tensor] = None, residual_period: int = 0,
+           residual_lo: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = act(x @ weight.T + bias) (+ residual).  x [M,K] bf16, weight [N,K] bf16, bias [N] fp32, residual [M,N] bf16 —
-    or, with residual_period = n > 0, a [n,N] table of which output row m adds row m % n (positional embedding)."""
-    _require_cuda(x, weight, bias, residual, out)
+    or, with residual_period = n > 0, a [n,N] table of which output row m adds row m % n (positional embedding).
+    Split residual stream: `residual_lo` is the low half of a (hi, lo) bf16 pair and `out_lo` (bf16 [M,N], written)
+    receives the low half of the sum; the returned tensor is the high half."""
+    _require_cuda(x, weight, bias, residual, out, residual_lo, out_lo)
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("linear: x and weight must be bf16")
     if bias is not None and bias.dtype != torch.float32:
         raise ValueError("linear: bias must be fp32")
-    if residual is not None and residual.dtype != torch.bfloat16:
-        raise ValueError("linear: residual must be bf16")
+    if any(t is not None and t.dtype != torch.bfloat16 for t in (residual, residual_lo, out_lo)):
+        raise ValueError("linear: residual / residual_lo / out_lo must be bf16")
     M, K = x.shape
     N, K2 = weight.shape
     if K != K2:
         raise ValueError(f"linear: K mismatch {K} vs {K2}")
     if residual is not None and tuple(residual.shape) != ((residual_period or M), N):
         raise ValueError("linear: residual shape mismatch")
+    if (residual_lo is not None or out_lo is not None) and (residual is None or gelu or residual_period):
+        raise ValueError("linear: the split (hi, lo) stream needs a plain residual GEMM")
+    if any(t is not None and tuple(t.shape) != (M, N) for t in (residual_lo, out_lo)):
+        raise ValueError("linear: residual_lo / out_lo shape mismatch")
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        if residual_period > 0:
+        if residual_period > 0 or residual_lo is not None or out_lo is not None:
             o = _lib.GemmOpts(bias=_ptr(bias), residual=_ptr(residual), act=1 if gelu else 0, cta_group=cta_group,
-                              residual_period=residual_period)
+                              residual_period=residual_period, residual_lo=_ptr(residual_lo), y_lo=_ptr(out_lo))
             check(_lib.load().mt_gemm_bf16_ex(x.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, o, _stream()),
                   "mt_gemm_bf16_ex")
         else:
@@ -81,15 +88,43 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out
 
 
-def row_stats(x: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Per-row LayerNorm statistics of x [M,d] (bf16/fp32): fp32 [M,2] = (mean, rstd)."""
-    _require_cuda(x, out)
+def split_f32(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> (hi, lo) bf16 pair with hi + lo = x to 16 mantissa bits (the residual-stream representation)."""
+    _require_cuda(x)
+    if x.dtype != torch.float32 or x.numel() % 4:
+        raise ValueError("split_f32: fp32 tensor with numel % 4 == 0")
+    hi = torch.empty_like(x, dtype=torch.bfloat16)
+    lo = torch.empty_like(x, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_split_f32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "mt_split_f32")
+    return hi, lo
+
+
+def merge_f32(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
+    """(hi, lo) bf16 pair -> fp32 hi + lo."""
+    _require_cuda(hi, lo)
+    if hi.dtype != torch.bfloat16 or lo.dtype != torch.bfloat16 or hi.shape != lo.shape or hi.numel() % 4:
+        raise ValueError("merge_f32: two bf16 tensors of the same shape, numel % 4 == 0")
+    out = torch.empty_like(hi, dtype=torch.float32)
+    with torch.cuda.device(hi.device):
+        check(_lib.load().mt_merge_f32(hi.data_ptr(), lo.data_ptr(), out.data_ptr(), hi.numel(), _stream()), "mt_merge_f32")
+    return out
+
+
+def row_stats(x: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
+              x_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-row LayerNorm statistics of x [M,d] (bf16/fp32; or of the split pair x + x_lo): fp32 [M,2] = (mean, rstd)."""
+    _require_cuda(x, out, x_lo)
     M, d = x.shape
     if out is None:
         out = torch.empty((M, 2), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(_lib.load().mt_row_stats(x.data_ptr(), _DT[x.dtype], out.data_ptr(), M, d, float(eps), _stream()),
-              "mt_row_stats")
+        if x_lo is not None:
+            check(_lib.load().mt_row_stats_split(x.data_ptr(), x_lo.data_ptr(), out.data_ptr(), M, d, float(eps), _stream()),
+                  "mt_row_stats_split")
+        else:
+            check(_lib.load().mt_row_stats(x.data_ptr(), _DT[x.dtype], out.data_ptr(), M, d, float(eps), _stream()),
+                  "mt_row_stats")
     return out
 
 

@@ -8,8 +8,9 @@ works on the published checkpoints.  Reference math: PointCloud/openpoints/model
 mlp.py:11-35 (verbatim timm copies).
 
 Precision model (documented in DESIGN.md): GEMM / attention operands bf16, fp32 accumulation, fp32 LayerNorm and
-softmax statistics, bf16 residual stream.  fp32 / fp16 inputs are converted at the module boundary and the result
-is returned in the input dtype.  There is NO CPU or eager fallback: CPU tensors, non-B200 devices or a missing
+softmax statistics; inside a Block the residual stream is a split hi + lo pair of bf16 tensors (16 mantissa bits).
+bf16 / fp16 inputs give a bf16-rounded Block output in the input dtype; fp32 inputs keep the split stream across
+Blocks (fp32 in, fp32 out, like the reference under autocast: fp32 residual, reduced-precision matmul operands).  There is NO CPU or eager fallback: CPU tensors, non-B200 devices or a missing
 extension raise.
 """
 from __future__ import annotations
@@ -208,7 +209,11 @@ class Block(nn.Module):
         cache[name] = (key, folded)
         return folded
 
-    def _forward_2d(self, x2: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    def _forward_2d(self, x2: torch.Tensor, B: int, N: int, x2_lo: Optional[torch.Tensor] = None,
+                    want_lo: bool = False):
+        """(hi, lo | None) of the Block output.  The residual stream is a split pair of bf16 tensors hi + lo (16 mantissa
+        bits, see mt_gemm.cu): x2_lo is the low half of the input (None for a bf16 input), the low half of the output is
+        produced when want_lo; inside the Block x_mid always carries its low half."""
         if not self.fold_layernorm:
             g1 = _packed(self, "norm1.weight", self.norm1.weight, torch.float32)
             b1 = _packed(self, "norm1.bias", self.norm1.bias, torch.float32)
@@ -217,24 +222,32 @@ class Block(nn.Module):
             h = ops.layernorm(x2, g1, b1, self.norm1.eps)
             x_mid = self.attn._forward_2d(h, B, N, residual=x2)
             h = ops.layernorm(x_mid, g2, b2, self.norm2.eps, out=h)
-            return self.mlp._forward_2d(h, residual=x_mid)
+            return self.mlp._forward_2d(h, residual=x_mid), None
         attn, mlp = self.attn, self.mlp
         wq, csq, bq = self._folded("fold.qkv", attn.qkv, self.norm1)
-        stats = ops.row_stats(x2, self.norm1.eps)
+        stats = ops.row_stats(x2, self.norm1.eps, x_lo=x2_lo)
         qkv = ops.linear_ln(x2, wq, bq, csq, stats)
         o = ops.attention(qkv.view(B, N, -1), attn.num_heads, attn.scale)
+        mid_lo = torch.empty_like(x2)
         x_mid = ops.linear(o.view(B * N, -1), _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16),
-                           _packed(attn, "proj.bias", attn.proj.bias, torch.float32), residual=x2)
+                           _packed(attn, "proj.bias", attn.proj.bias, torch.float32), residual=x2, residual_lo=x2_lo,
+                           out_lo=mid_lo)
         w1, cs1, b1 = self._folded("fold.fc1", mlp.fc1, self.norm2)
-        stats = ops.row_stats(x_mid, self.norm2.eps, out=stats)
+        stats = ops.row_stats(x_mid, self.norm2.eps, out=stats, x_lo=mid_lo)
         hid = ops.linear_ln(x_mid, w1, b1, cs1, stats, gelu=True)
-        return ops.linear(hid, _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16),
-                          _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32), residual=x_mid)
+        out_lo = torch.empty_like(x2) if want_lo else None
+        out = ops.linear(hid, _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16),
+                         _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32), residual=x_mid, residual_lo=mid_lo,
+                         out_lo=out_lo)
+        return out, out_lo
 
-    def _transposed(self, name: str, w: torch.Tensor) -> torch.Tensor:
-        """bf16 [in, out] copy of a packed bf16 [out, in] weight: the B operand of the dgrad GEMM  dX = dY @ W."""
+    def _transposed(self, name: str, w: torch.Tensor, *sources: Optional[torch.Tensor]) -> torch.Tensor:
+        """bf16 [in, out] copy of a packed bf16 [out, in] weight: the B operand of the dgrad GEMM  dX = dY @ W.
+        Cached on the SOURCE parameters' (storage, version, device, dtype) — the same key `_packed` / `_folded` use — so
+        the transpose is rebuilt whenever they are: the packed tensor itself comes from torch.empty (version always 0,
+        addresses recycled by the caching allocator) and cannot tell two weights apart."""
         cache = self.__dict__.setdefault("_mt_pack_cache", {})
-        key = (w.data_ptr(), w._version, w.device)
+        key = tuple(None if q is None else (q.data_ptr(), q._version, q.device, q.dtype) for q in sources)
         hit = cache.get(name)
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -311,19 +324,19 @@ class Block(nn.Module):
         M = B * N
         # gradient entering the mlp branch (after its dropout / stochastic depth, replayed from the saved Philox keys)
         gb2 = g2 if drop is None else self._replay(g2, drop["p_mlp"], drop["k2"], drop["rs2"], N)
-        w2t = self._transposed("t.fc2", _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16))
+        w2t = self._transposed("t.fc2", _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16), mlp.fc2.weight)
         du = ops.linear_gelu_grad(gb2, w2t, u)                                  # dL/du = (g W2) * gelu'(u)
         if drop is not None and drop["p_mlp"] > 0:
             du = ops.dropout(du, drop["p_mlp"], *drop["kh"], out=du)            # the mask sits between gelu and fc2
         w1f = self._folded("fold.fc1", mlp.fc1, self.norm2)[0]
-        dxh2 = ops.linear(du, self._transposed("t.fc1f", w1f))                  # dL/dxhat (gamma already folded in)
+        dxh2 = ops.linear(du, self._transposed("t.fc1f", w1f, mlp.fc1.weight, self.norm2.weight))                  # dL/dxhat (gamma already folded in)
         g1 = ops.layernorm_bwd(dxh2, x_mid, stats2, None, add=g2)               # + residual branch
         gb1 = g1 if drop is None else self._replay(g1, drop["p_proj"], drop["k1"], drop["rs1"], N)
-        wpt = self._transposed("t.proj", _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16))
+        wpt = self._transposed("t.proj", _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16), attn.proj.weight)
         do = ops.linear(gb1, wpt)
         dqkv = ops.attention_bwd(qkv.view(B, N, -1), o, do.view(B, N, -1), lse2, attn.num_heads, attn.scale)
         wqf = self._folded("fold.qkv", attn.qkv, self.norm1)[0]
-        dxh1 = ops.linear(dqkv.view(M, -1), self._transposed("t.qkvf", wqf))
+        dxh1 = ops.linear(dqkv.view(M, -1), self._transposed("t.qkvf", wqf, attn.qkv.weight, self.norm1.weight))
         dx = ops.layernorm_bwd(dxh1, x2, stats1, None, add=g1)
         return dx, (gb2, du, gb1, dqkv.view(M, -1))
 
@@ -382,7 +395,14 @@ class Block(nn.Module):
         B, N, C = x.shape
         if self._is_stochastic():                               # train mode without autograd: masks still apply
             return _from_bf16(self._forward_train(_to_bf16_2d(x), B, N)[0], x)
-        return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N), x)
+        if x.dtype == torch.float32 and self.fold_layernorm and x.numel() % 4 == 0:
+            # fp32 caller (autocast-style: fp32 residual stream, bf16 tensor-core operands): the stream enters and leaves
+            # the Block as a split hi + lo pair, so a Sequential of Blocks accumulates its 2L residual adds in fp32
+            x2 = x.reshape(-1, C)
+            hi, lo = ops.split_f32(x2 if x2.is_contiguous() else x2.contiguous())
+            out_hi, out_lo = self._forward_2d(hi, B, N, lo, want_lo=True)
+            return ops.merge_f32(out_hi, out_lo).view(B, N, C)
+        return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N)[0], x)
 
 
 class _BlockFn(torch.autograd.Function):
