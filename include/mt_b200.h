@@ -195,6 +195,14 @@ int mt_pool_layernorm_bwd(const void* dy, const void* x, const float* gamma, voi
 int mt_dropout(const void* x, const void* residual, const float* row_scale, int rows_per_scale, void* out,
                long long rows, int d, float p, unsigned long long seed, unsigned long long offset, void* stream);
 
+/* ---- embedding-bag sum: out[r,:] = pos[r % pos_period,:] + sum_f table[idx[r,f] + offsets[f], :] -----------------------
+ * table fp32 [V,d] (several nn.Embedding weights concatenated row-wise, `offsets` = first row of each, or NULL), idx
+ * int32 [rows,F], pos fp32 [pos_period,d] or NULL, out bf16 / fp32 [rows,d].  Calendar embeddings of the time-series
+ * tokenizer (Data2Seq/Time_Series.py:64-92,120-126) and atom / bond feature sums of the graph tokenizer
+ * (Data2Seq/Graph.py:254-255).                                                                                    */
+int mt_embed_sum(const float* table, const int* idx, const int* offsets, int F, const float* pos, int pos_period,
+                 void* out, int out_dtype, long long rows, int d, void* stream);
+
 /* ---- text features: zero padding to the encoder width (Data2Seq/Text.py:15-19); dtype fp32 or bf16 ---- */
 int mt_pad_cols(const void* x, void* out, int dtype, long long rows, int c_in, int c_out, void* stream);
 

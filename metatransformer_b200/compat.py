@@ -32,6 +32,11 @@ def install(force_timm: bool = False) -> None:
         layers = types.ModuleType("timm.models.layers")
         layers.DropPath = vision_transformer.DropPath
         layers.to_2tuple = lambda x: tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+        # initialisers the reference forks import from timm.models.layers (Video/models/modeling_finetune.py:15,
+        # Audio/src/models/ast_models.py:13): torch's own implementations
+        import torch.nn as _nn
+        layers.trunc_normal_ = _nn.init.trunc_normal_
+        layers.lecun_normal_ = lambda t: _nn.init.trunc_normal_(t, std=(1.0 / max(1, t.shape[-1])) ** 0.5)
         timm.models = models
         models.vision_transformer = vision_transformer
         models.layers = layers
@@ -39,5 +44,5 @@ def install(force_timm: bool = False) -> None:
                             "timm.models.vision_transformer": vision_transformer})
     # `from Data2Seq import Data2Seq` (reference scripts run with Data2Seq/ on sys.path, Data2Seq.py:9-15)
     sys.modules.setdefault("Data2Seq", importlib.import_module(data2seq.__name__ + ".Data2Seq"))
-    for name in ("Image", "Video", "Acoustic", "Time_Series", "Hyper_Spectrum"):
+    for name in ("Image", "Video", "Acoustic", "Time_Series", "Hyper_Spectrum", "Text"):
         sys.modules.setdefault(name, getattr(data2seq, name))

@@ -6,16 +6,24 @@
 // Blackwell design (sm_100a only), head_dim = 64, no mask, no dropout:
 //   * q, k, v are read straight out of the packed (B, N, 3, H, 64) qkv buffer through one 4-D TMA descriptor
 //     (no permute / contiguous copies), output is written straight into (B, N, H*64) through a 4-D TMA store;
-//   * persistent CTAs; a work item is (batch, head, 256 query rows) = two 128-row query tiles that ping-pong:
-//     while the softmax warps of tile 0 work on S0, the tensor core computes S1 / P1·V, and vice versa;
+//   * persistent CTAs, TWO per SM (108 KB of shared memory, 256 TMEM columns, 96 registers per softmax thread each):
+//     the kernel is bound by the softmax warps' instruction latency and by MUFU (one ex2 per score: 16 / clk / SM is
+//     the same 47 us floor as the HBM traffic at C2), so what counts is how many independent softmax instruction
+//     streams an SM scheduler can pick from — 4 warps per scheduler here against 2 in the one-CTA-per-SM version;
+//   * a work item is (batch, head, 256 query rows) = two 128-row query tiles that ping-pong: while the softmax warps
+//     of tile 0 work on S0, the tensor core computes S1 / P1·V, and vice versa; warps whose 32 query rows all lie
+//     beyond N only keep the barrier protocol going;
 //   * S = Q·K^T and O += P·V are tcgen05.mma (bf16 in, fp32 accumulate) with S and O living in TMEM
-//     (S0,S1: 2 x 128 columns, O0,O1: 2 x 64 columns); V is consumed as an MN-major operand so no transpose;
+//     (S0,S1: 2 x 64 columns, O0,O1: 2 x 64 columns); V is consumed as an MN-major operand so no transpose;
 //   * online softmax in fp32 registers, one query row per thread (tcgen05.ld 32x32b), exp2 with the
-//     scale*log2(e) factor folded in; P goes back as bf16 through 128B-swizzled smem;
-//   * K/V tiles (128 keys) stream through 3-stage TMA rings shared by both query tiles.
+//     scale*log2(e) factor folded in; P goes back as bf16 through 128B-swizzled smem; the last key tile is
+//     processed in 16-key quarters (N = 196: 4 valid keys -> one quarter);
+//   * K/V tiles (64 keys) stream through 3- / 2-stage TMA rings shared by both query tiles.
 //
 // Warps (384 threads): 0-3 softmax tile 0, 4-7 softmax tile 1 (warp%4 = TMEM lane quarter), 8 = TMA loader,
 // 9 = S=QK^T issuer + TMEM allocator, 10 = O+=PV issuer, 11 idle (completes the third warpgroup for setmaxnreg).
+// a timed-out barrier wait traps without the device printf: the call sequence costs the 40-register role warps spills
+#define MT_WAIT_QUIET 1
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 
@@ -23,24 +31,26 @@ namespace mt {
 
 constexpr int kAtQT = 2;                    // query tiles per CTA
 constexpr int kAtBM = 128;                  // query rows per tile
-constexpr int kAtBN = 128;                  // keys per KV tile
+constexpr int kAtBN = 64;                   // keys per KV tile
 constexpr int kAtD = 64;                    // head dim
-constexpr int kAtStages = 3;
-constexpr int kAtThreads = 32 * (4 * kAtQT + 4);  // warps 10, 11 only pad the third warpgroup (setmaxnreg)
-constexpr int kAtTileBytes = 128 * 64 * 2;  // 16 KB: any 128 x 64 bf16 tile
-constexpr int kAtQBufs = 2;                 // Q tiles are double-buffered across work items
+constexpr int kAtKStages = 3;
+constexpr int kAtVStages = 2;
+constexpr int kAtThreads = 32 * (4 * kAtQT + 4);
+constexpr int kAtQBytes = kAtBM * kAtD * 2;   // 16 KB: a 128 x 64 bf16 tile (Q_t, P_t)
+constexpr int kAtKVBytes = kAtBN * kAtD * 2;  //  8 KB: a 64 x 64 bf16 tile (K_j, V_j)
 constexpr int kAtSmemQ = 0;
-constexpr int kAtSmemK = kAtSmemQ + kAtQBufs * kAtQT * kAtTileBytes;
-constexpr int kAtSmemV = kAtSmemK + kAtStages * kAtTileBytes;
-constexpr int kAtSmemP = kAtSmemV + kAtStages * kAtTileBytes;           // per q-tile: 2 chunks of 64 keys
-constexpr int kAtSmemBar = kAtSmemP + kAtQT * 2 * kAtTileBytes;
-// barriers: q_full[4] q_empty[4] k_full[3] k_empty[3] v_full[3] v_empty[3] s_full[2] s_empty[2] p_full[2] o_done[2]
-constexpr int kAtNumBars = 2 * kAtQBufs * kAtQT + 4 * kAtStages + 4 * kAtQT;
+constexpr int kAtSmemP = kAtSmemQ + kAtQT * kAtQBytes;
+constexpr int kAtSmemK = kAtSmemP + kAtQT * kAtQBytes;
+constexpr int kAtSmemV = kAtSmemK + kAtKStages * kAtKVBytes;
+constexpr int kAtSmemBar = kAtSmemV + kAtVStages * kAtKVBytes;
+// barriers: q_full[2] q_empty[2] k_full[3] k_empty[3] v_full[2] v_empty[2] s_full[2] s_empty[2] p_full[2] o_done[2]
+constexpr int kAtNumBars = 2 * kAtQT + 2 * kAtKStages + 2 * kAtVStages + 4 * kAtQT;
 constexpr int kAtSmemTmemPtr = kAtSmemBar + kAtNumBars * 8;
-constexpr int kAtSmemBytes = kAtSmemTmemPtr + 16 + 1024;
-constexpr int kAtTmemCols = 512;
-constexpr int kAtTmemS = 0;     // S_t at columns 128*t
-constexpr int kAtTmemO = 256;   // O_t at columns 256 + 64*t
+constexpr int kAtSmemBytes = kAtSmemTmemPtr + 16 + 1024;   // 107.7 KB: two CTAs per SM
+constexpr int kAtTmemCols = 256;   // two CTAs per SM share the 512 columns
+constexpr int kAtTmemS = 0;        // S_t at columns 64*t
+constexpr int kAtTmemO = 128;      // O_t at columns 128 + 64*t
+static_assert(2 * (kAtSmemBytes + 1024) <= 233472, "two attention CTAs must fit one SM's shared memory");
 
 MT_DEVINL float ex2_approx(float x) {
   float y;
@@ -51,16 +61,16 @@ MT_DEVINL float ex2_approx(float x) {
 struct AttnParams {
   int B, N, H;
   int num_qp;        // ceil(N / 256)
-  int num_kv;        // ceil(N / 128)
+  int num_kv;        // ceil(N / 64)
   int num_items;     // B * H * num_qp
   float scale_log2;  // scale * log2(e)
   float* lse2;       // optional [B, H, N]: log2-sum-exp of the scaled scores (m*c + log2 l), saved for the backward
   unsigned long long* tl;   // optional timeline slot (mt_timeline_begin)
 };
 
-__global__ void __launch_bounds__(kAtThreads, 1)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out,
-                     const AttnParams p) {
+__global__ void __launch_bounds__(kAtThreads, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                     const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -68,36 +78,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   const int lane = threadIdx.x & 31;
 
   const uint32_t bar0 = smem_base + kAtSmemBar;
-  auto q_full = [&](int qb, int t) { return bar0 + 8u * (0 + 2 * qb + t); };
-  auto q_empty = [&](int qb, int t) { return bar0 + 8u * (4 + 2 * qb + t); };
-  auto k_full = [&](int s) { return bar0 + 8u * (8 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (11 + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (14 + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (17 + s); };
-  auto s_full = [&](int t) { return bar0 + 8u * (20 + t); };
-  auto s_empty = [&](int t) { return bar0 + 8u * (22 + t); };
-  auto p_full = [&](int t) { return bar0 + 8u * (24 + t); };
-  auto o_done = [&](int t) { return bar0 + 8u * (26 + t); };
-  auto q_smem = [&](int qb, int t) { return smem_base + uint32_t(kAtSmemQ + (2 * qb + t) * kAtTileBytes); };
+  auto q_full = [&](int t) { return bar0 + 8u * (0 + t); };
+  auto q_empty = [&](int t) { return bar0 + 8u * (2 + t); };
+  auto k_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (4 + kAtKStages + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (4 + 2 * kAtKStages + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (4 + 2 * kAtKStages + kAtVStages + s); };
+  constexpr int kB2 = 4 + 2 * kAtKStages + 2 * kAtVStages;
+  auto s_full = [&](int t) { return bar0 + 8u * (kB2 + t); };
+  auto s_empty = [&](int t) { return bar0 + 8u * (kB2 + 2 + t); };
+  auto p_full = [&](int t) { return bar0 + 8u * (kB2 + 4 + t); };
+  auto o_done = [&](int t) { return bar0 + 8u * (kB2 + 6 + t); };
+  auto q_smem = [&](int t) { return smem_base + uint32_t(kAtSmemQ + t * kAtQBytes); };
   const uint32_t tmem_ptr_addr = smem_base + kAtSmemTmemPtr;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kAtSmemTmemPtr);
 
   if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_out);
     for (int t = 0; t < kAtQT; ++t) {
-      for (int qb = 0; qb < kAtQBufs; ++qb) {
-        mbar_init(q_full(qb, t), 1);
-        mbar_init(q_empty(qb, t), 1);
-      }
+      mbar_init(q_full(t), 1);
+      mbar_init(q_empty(t), 1);
       mbar_init(s_full(t), 1);
       mbar_init(s_empty(t), 4);  // one arrive per softmax warp
       mbar_init(p_full(t), 4);
       mbar_init(o_done(t), 1);
     }
-    for (int s = 0; s < kAtStages; ++s) {
+    for (int s = 0; s < kAtKStages; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
+    }
+    for (int s = 0; s < kAtVStages; ++s) {
       mbar_init(v_full(s), 1);
       mbar_init(v_empty(s), 1);
     }
@@ -115,74 +127,72 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   const int H = p.H;
 
-  // register re-distribution between warpgroups (compiled for 168/thread): the softmax warpgroups hold a whole
-  // 128-column score row per thread, the loader / MMA warpgroup needs almost nothing
+  // register re-distribution between warpgroups (compiled for 80/thread: two CTAs per SM): the softmax warpgroups hold
+  // a whole 64-column score row per thread, the loader / MMA warpgroup needs almost nothing
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
     // =============================== TMA loader =================================
     if (lane == 0) {
       int kst = 0; uint32_t kph = 0;
       int vst = 0; uint32_t vph = 0;
       uint32_t it = 0;
+      // K / V of a (batch, head) are read once per 256-query item: keep them in L2 only when there are several items
+      const uint64_t kv_hint = (p.num_qp > 1) ? kEvictLast : kEvictFirst;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int qp = item % p.num_qp;
         const int bh = item / p.num_qp;
         const int h = bh % H, b = bh / H;
-        const int qb = int(it & 1u);
         for (int t = 0; t < kAtQT; ++t) {
-          mbar_wait(q_empty(qb, t), ((it >> 1) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(q_full(qb, t), kAtTileBytes);
-          tma_load_4d(q_smem(qb, t), &tm_qkv, q_full(qb, t), 0, h, qp * 256 + t * 128, b, kEvictFirst);
+          mbar_wait(q_empty(t), (it & 1u) ^ 1u);
+          mbar_arrive_expect_tx(q_full(t), kAtQBytes);
+          tma_load_4d(q_smem(t), &tm_q, q_full(t), 0, h, qp * 256 + t * 128, b, kEvictFirst);
         }
         for (int j = 0; j < p.num_kv; ++j) {
           mbar_wait(k_empty(kst), kph ^ 1u);
-          mbar_arrive_expect_tx(k_full(kst), kAtTileBytes);
-          tma_load_4d(smem_base + kAtSmemK + kst * kAtTileBytes, &tm_qkv, k_full(kst), 0, H + h, j * kAtBN, b,
-                      kEvictLast);
-          if (++kst == kAtStages) { kst = 0; kph ^= 1u; }
+          mbar_arrive_expect_tx(k_full(kst), kAtKVBytes);
+          tma_load_4d(smem_base + kAtSmemK + kst * kAtKVBytes, &tm_kv, k_full(kst), 0, H + h, j * kAtBN, b, kv_hint);
+          if (++kst == kAtKStages) { kst = 0; kph ^= 1u; }
           mbar_wait(v_empty(vst), vph ^ 1u);
-          mbar_arrive_expect_tx(v_full(vst), kAtTileBytes);
-          tma_load_4d(smem_base + kAtSmemV + vst * kAtTileBytes, &tm_qkv, v_full(vst), 0, 2 * H + h, j * kAtBN, b,
-                      kEvictLast);
-          if (++vst == kAtStages) { vst = 0; vph ^= 1u; }
+          mbar_arrive_expect_tx(v_full(vst), kAtKVBytes);
+          tma_load_4d(smem_base + kAtSmemV + vst * kAtKVBytes, &tm_kv, v_full(vst), 0, 2 * H + h, j * kAtBN, b,
+                      kv_hint);
+          if (++vst == kAtVStages) { vst = 0; vph ^= 1u; }
         }
       }
     }
   } else if (warp == 9) {
     // =============================== S = Q K^T issuer ============================
-    // Two single-thread MMA issuers (this warp and warp 10) instead of one: issuing ~44 tcgen05.mma per work item
-    // from one thread (descriptor arithmetic + barrier polls are a serial dependency chain) was the critical path.
-    // This thread runs ahead on its own, throttled only by s_empty (the softmax warps pulled S_t into registers):
-    // the first score tile of the next work item is computed while the current item is still in its softmax.
+    // Two single-thread MMA issuers (this warp and warp 10) instead of one: the tcgen05.mma of a work item issued from one
+    // thread (descriptor arithmetic + barrier polls are a serial dependency chain) were the critical path.
+    // This thread runs ahead on its own, throttled only by s_empty (the softmax warps pulled S_t into registers).
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(kAtBM, kAtBN, 0, 0);   // both operands K-major
       int kst = 0; uint32_t kph = 0;
       uint32_t n_s0 = 0, n_s1 = 0;   // S_t tiles issued so far
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const int qb = int(it & 1u);
         for (int j = 0; j < p.num_kv; ++j) {
           mbar_wait(k_full(kst), kph);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_base + kAtSmemK + kst * kAtTileBytes);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_base + kAtSmemK + kst * kAtKVBytes);
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
-            if (j == 0) mbar_wait(q_full(qb, t), (it >> 1) & 1u);
+            if (j == 0) mbar_wait(q_full(t), it & 1u);
             uint32_t& n_s = (t == 0) ? n_s0 : n_s1;
             mbar_wait(s_empty(t), (n_s & 1u) ^ 1u);
             ++n_s;
             tc_fence_after();
-            const uint64_t adesc = make_smem_desc_sw128(q_smem(qb, t));
+            const uint64_t adesc = make_smem_desc_sw128(q_smem(t));
             const uint32_t d_tmem = tmem_base + kAtTmemS + t * kAtBN;
             umma_f16_ss<1>(d_tmem, adesc, bdesc, idesc_s, 0u);
             umma_f16_ss<1>(d_tmem, adesc + 2u, bdesc + 2u, idesc_s, 1u);
             umma_f16_ss<1>(d_tmem, adesc + 4u, bdesc + 4u, idesc_s, 1u);
             umma_f16_ss<1>(d_tmem, adesc + 6u, bdesc + 6u, idesc_s, 1u);
             umma_commit(s_full(t));
-            if (j + 1 == p.num_kv) umma_commit(q_empty(qb, t));   // last use of Q_t for this item
+            if (j + 1 == p.num_kv) umma_commit(q_empty(t));   // last use of Q_t for this item
           }
           umma_commit(k_empty(kst));
-          if (++kst == kAtStages) { kst = 0; kph ^= 1u; }
+          if (++kst == kAtKStages) { kst = 0; kph ^= 1u; }
         }
       }
     }
@@ -195,45 +205,44 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         for (int j = 0; j < p.num_kv; ++j) {
           const int valid = min(kAtBN, p.N - j * kAtBN);
-          const int ksteps = 2 * ((valid + 31) / 32);  // 16-key steps covering the valid 32-key chunks
+          const int ksteps = (valid + 15) >> 4;   // 16-key steps covering the valid keys
           mbar_wait(v_full(vst), vph);
-          const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + kAtSmemV + vst * kAtTileBytes);
+          const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + kAtSmemV + vst * kAtKVBytes);
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
             uint32_t& n_p = (t == 0) ? n_p0 : n_p1;
             mbar_wait(p_full(t), n_p & 1u);
             ++n_p;
             tc_fence_after();
-            const uint64_t adesc0 = make_smem_desc_sw128(smem_base + kAtSmemP + t * 2 * kAtTileBytes);
+            const uint64_t adesc0 = make_smem_desc_sw128(smem_base + kAtSmemP + t * kAtQBytes);
             const uint32_t d_tmem = tmem_base + kAtTmemO + t * kAtD;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 4; ++k) {
               if (k < ksteps) {
-                // A: P chunk (k / 4) is 16 KB further, 32 B per 16-key step inside a 128 B row;
+                // A: 32 B per 16-key step inside P's 128 B rows;
                 // B: 16 keys = 16 rows of 128 B = 2 KB per step (descriptor address field is in 16-byte units)
-                const uint64_t adesc = adesc0 + uint64_t((k >> 2) * (kAtTileBytes >> 4) + 2 * (k & 3));
-                const uint64_t bdesc = bdesc0 + uint64_t(k * (16 * 128 >> 4));
-                umma_f16_ss<1>(d_tmem, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                umma_f16_ss<1>(d_tmem, adesc0 + uint64_t(2 * k), bdesc0 + uint64_t(k * (16 * 128 >> 4)), idesc_o,
+                               (j > 0 || k > 0) ? 1u : 0u);
               }
             }
             umma_commit(o_done(t));
           }
           umma_commit(v_empty(vst));
-          if (++vst == kAtStages) { vst = 0; vph ^= 1u; }
+          if (++vst == kAtVStages) { vst = 0; vph ^= 1u; }
         }
       }
     }
   }
   } else {
     // =============================== softmax warps ==============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     const int t = warp >> 2;        // query tile
     const int q = warp & 3;         // TMEM lane quarter
     const int r_in_tile = 32 * q + lane;
     const uint32_t lane_off = uint32_t(32 * q) << 16;
     const uint32_t ts = tmem_base + lane_off + uint32_t(kAtTmemS + t * kAtBN);
     const uint32_t to = tmem_base + lane_off + uint32_t(kAtTmemO + t * kAtD);
-    const uint32_t pbase = smem_base + kAtSmemP + t * 2 * kAtTileBytes;
+    const uint32_t pbase = smem_base + kAtSmemP + t * kAtQBytes;
     const uint32_t prow = pbase + uint32_t(r_in_tile * 128);
     const uint32_t swz = uint32_t(r_in_tile & 7);
     uint32_t n_sf = 0, n_od = 0;
@@ -244,52 +253,61 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       const int qp = item % p.num_qp;
       const int bh = item / p.num_qp;
       const int h = bh % H, b = bh / H;
+      const int row0 = qp * 256 + t * 128 + 32 * q;     // first query row of this warp
+      if (row0 >= p.N) {
+        // No valid query row in this warp (N = 196: the last warp of the second tile): keep the barrier protocol going,
+        // skip all the arithmetic.  Its rows of P_t stay garbage, which only feeds rows of O_t that are never stored.
+        for (int j = 0; j < p.num_kv; ++j) {
+          mbar_wait(s_full(t), n_sf & 1u);
+          ++n_sf;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty(t));
+          if (j > 0) { mbar_wait(o_done(t), n_od & 1u); ++n_od; }
+          if (store_pending) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            store_pending = false;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full(t));
+        }
+        mbar_wait(o_done(t), n_od & 1u);
+        ++n_od;
+        continue;
+      }
       float m_run = -INFINITY;
       float l_run = 0.f;
 
       for (int j = 0; j < p.num_kv; ++j) {
         const int valid = min(kAtBN, p.N - j * kAtBN);
-        const int nfull = valid >> 5;        // 32-key chunks without padding
-        const int tail = valid & 31;         // valid keys of the last, partially padded chunk (0 = none)
+        const int nq = (valid + 15) >> 4;    // 16-key quarters that hold valid keys
+        const int tail = valid & 15;         // valid keys of the last, partially padded quarter (0 = none)
         mbar_wait(s_full(t), n_sf & 1u);
         ++n_sf;
         tc_fence_after();
-        uint32_t s[128];
-        // the padded chunk (runtime TMEM column 32*nfull) always lands in s[96..127]: that slot is only needed by a
-        // fourth full chunk, and then there is no padded chunk
-        if (nfull > 0) tmem_ld_32x32b_x32_at<0>(ts, s);
-        if (nfull > 1) tmem_ld_32x32b_x32_at<32>(ts + 32u, s);
-        if (nfull > 2) tmem_ld_32x32b_x32_at<64>(ts + 64u, s);
-        if (nfull > 3) tmem_ld_32x32b_x32_at<96>(ts + 96u, s);
-        if (tail) tmem_ld_32x32b_x32_at<96>(ts + uint32_t(32 * nfull), s);
-        tmem_wait_ld();
-        // S_t is in registers: the tensor core may overwrite it with the next tile's scores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(t));
-
-        // ---- running max ----
+        // ---- pass 1: row maximum straight from TMEM, one 16-key quarter at a time (a whole 64-column score row plus
+        //      the exp / pack temporaries does not fit the 96 registers a two-CTA-per-SM softmax thread has; TMEM reads
+        //      are cheap, so pass 2 simply loads the quarters again).  Padded keys of the last quarter -> -inf. ----
         float m_tile = -INFINITY;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < nfull) {
+        for (int qi = 0; qi < 4; ++qi) {
+          if (qi < nq) {
+            uint32_t sq[16];
+            tmem_ld_32x32b_x16(ts + uint32_t(16 * qi), sq);
+            tmem_wait_ld();
+            if (tail != 0 && qi == nq - 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(s[32 * ch + i]));
-          }
-        }
-        if (tail) {
+              for (int i = 0; i < 16; ++i) m_tile = fmaxf(m_tile, (i < tail) ? __uint_as_float(sq[i]) : -INFINITY);
+            } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = (i < tail) ? __uint_as_float(s[96 + i]) : -INFINITY;   // padded keys (zero K rows) -> -inf
-            s[96 + i] = __float_as_uint(v);
-            m_tile = fmaxf(m_tile, v);
+              for (int i = 0; i < 16; i += 2)
+                m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(sq[i]), __uint_as_float(sq[i + 1])));
+            }
           }
         }
         // Lazy rescaling: the running maximum is only advanced (and O_t rescaled) when some row of this warp saw its
         // maximum grow by more than 2^kLazyLog2; otherwise the stale maximum keeps being the reference — P may then
         // exceed 1 (by at most 2^kLazyLog2, harmless in fp32 / bf16) and O / l at the end is unchanged mathematically.
-        // With 128-key tiles the maximum almost never jumps that far after the first tile, so the TMEM round trip
-        // of O_t disappears from the critical path.
         constexpr float kLazyLog2 = 8.0f;
         const bool grow = (j > 0) && __any_sync(0xffffffffu, (m_tile - m_run) * c > kLazyLog2);
         const float m_new = (j == 0) ? m_tile : (grow ? fmaxf(m_run, m_tile) : m_run);
@@ -307,18 +325,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
             // rescale the running output by alpha
             const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t o[32];
-              tmem_ld_32x32b_x32(to + uint32_t(32 * hh), o);
+            for (int hh = 0; hh < 4; ++hh) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(to + uint32_t(16 * hh), o);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
+              for (int i = 0; i < 16; i += 2) {
                 float a0, a1;
                 unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), a0, a1);
                 o[i] = __float_as_uint(a0);
                 o[i + 1] = __float_as_uint(a1);
               }
-              tmem_st_32x32b_x32(to + uint32_t(32 * hh), o);
+              tmem_st_32x32b_x16(to + uint32_t(16 * hh), o);
             }
             tmem_wait_st();
           }
@@ -329,52 +347,45 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           __syncwarp();
           store_pending = false;
         }
-        // ---- P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V) ----
+        // ---- pass 2: P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V) ----
         uint64_t l2 = pack_f32x2(0.f, 0.f);   // two partial row sums (even / odd keys), packed fp32x2 adds
         const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          if (ch < nfull) {
+        for (int qi = 0; qi < 4; ++qi) {
+          if (qi < nq) {
+            uint32_t sq[16];
+            tmem_ld_32x32b_x16(ts + uint32_t(16 * qi), sq);
+            tmem_wait_ld();
+            if (qi == nq - 1) {
+              // the last read of S_t: the tensor core may overwrite it with the next tile's scores
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_empty(t));
+              if (tail != 0) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {  // four 16-byte groups (8 keys each) per 32-key chunk
+                for (int i = 0; i < 16; ++i)
+                  if (i >= tail) sq[i] = 0xff800000u;   // -inf: exp2 gives 0 for the padded keys
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {  // two 16-byte groups (8 keys each) per 16-key quarter
               uint32_t pk[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float a0, a1;
-                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[32 * ch + 8 * g + 2 * i]),
-                                                  __uint_as_float(s[32 * ch + 8 * g + 2 * i + 1])), c2, nmc2), a0, a1);
+                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sq[8 * g + 2 * i]), __uint_as_float(sq[8 * g + 2 * i + 1])),
+                                       c2, nmc2), a0, a1);
                 const float e0 = ex2_approx(a0);
                 const float e1 = ex2_approx(a1);
                 l2 = add_f32x2(l2, pack_f32x2(e0, e1));
                 pk[i] = pack_bf16x2(e0, e1);
               }
-              const uint32_t chunk16 = uint32_t((ch & 1) * 4 + g);
-              const uint32_t addr = prow + uint32_t((ch >> 1) * kAtTileBytes) + ((chunk16 ^ swz) << 4);
+              const uint32_t chunk16 = uint32_t(2 * qi + g);
+              const uint32_t addr = prow + ((chunk16 ^ swz) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                            "r"(pk[3])
                            : "memory");
             }
-          }
-        }
-        if (tail) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float a0, a1;
-              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[96 + 8 * g + 2 * i]), __uint_as_float(s[96 + 8 * g + 2 * i + 1])),
-                                     c2, nmc2), a0, a1);
-              const float e0 = ex2_approx(a0);   // exp2(-inf) = 0
-              const float e1 = ex2_approx(a1);
-              l2 = add_f32x2(l2, pack_f32x2(e0, e1));
-              pk[i] = pack_bf16x2(e0, e1);
-            }
-            const uint32_t chunk16 = uint32_t((nfull & 1) * 4 + g);
-            const uint32_t addr = prow + uint32_t((nfull >> 1) * kAtTileBytes) + ((chunk16 ^ swz) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                         "r"(pk[3])
-                         : "memory");
           }
         }
         float l_lo, l_hi;
@@ -386,7 +397,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         if (lane == 0) mbar_arrive(p_full(t));
       }
 
-      // ---- epilogue: O_t / l -> bf16 -> staged in this warp's rows of P_t chunk 0 -> TMA store ----
+      // ---- epilogue: O_t / l -> bf16 -> staged in this warp's rows of P_t -> TMA store ----
       mbar_wait(o_done(t), n_od & 1u);
       ++n_od;
       tc_fence_after();
@@ -396,31 +407,30 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         const int qrow = qp * 256 + t * 128 + r_in_tile;
         if (p.lse2 != nullptr && qrow < p.N) p.lse2[(size_t(b) * H + h) * p.N + qrow] = fmaf(m_run, c, log2f(l_run));
       }
-      uint32_t ob[32];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t o[32];
         tmem_ld_32x32b_x32(to + uint32_t(32 * hh), o);
         tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a0, a1;
-          unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), inv_l2), a0, a1);
-          ob[(32 * hh + i) >> 1] = pack_bf16x2(a0, a1);
+        for (int g = 0; g < 4; ++g) {
+          uint32_t ob[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a0, a1;
+            unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[8 * g + 2 * i]), __uint_as_float(o[8 * g + 2 * i + 1])), inv_l2),
+                         a0, a1);
+            ob[i] = pack_bf16x2(a0, a1);
+          }
+          const uint32_t addr = prow + ((uint32_t(4 * hh + g) ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ob[0]), "r"(ob[1]), "r"(ob[2]), "r"(ob[3])
+                       : "memory");
         }
       }
       tc_fence_before();
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint32_t addr = prow + ((uint32_t(g) ^ swz) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(ob[4 * g + 0]), "r"(ob[4 * g + 1]),
-                     "r"(ob[4 * g + 2]), "r"(ob[4 * g + 3])
-                     : "memory");
-      }
       fence_proxy_async_smem();
       __syncwarp();
-      const int row0 = qp * 256 + t * 128 + 32 * q;
-      if (lane == 0 && row0 < p.N) {
+      if (lane == 0) {
         tma_store_4d(&tm_out, pbase + uint32_t(32 * q * 128), 0, h, row0, b);
         tma_store_commit();
       }
@@ -455,14 +465,17 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
   MT_REQUIRE(scale > 0.f, MT_ERR_UNSUPPORTED, "mt_attention_fwd: scale must be positive");
   MT_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, MT_ERR_BAD_ALIGN,
              "mt_attention_fwd: pointers must be 16-byte aligned");
-  CUtensorMap tm_qkv, tm_out;
+  CUtensorMap tm_q, tm_kv, tm_out;
   {
-    // (B, N, 3, H, 64) viewed as dims [64, 3H, N, B]
+    // (B, N, 3, H, 64) viewed as dims [64, 3H, N, B]; 128-row boxes for Q tiles, 64-row boxes for K / V tiles
     uint64_t dims[4] = {64, uint64_t(3 * H), uint64_t(N), uint64_t(B)};
     uint64_t strides[3] = {64 * 2, uint64_t(3 * H) * 64 * 2, uint64_t(N) * 3 * H * 64 * 2};
-    uint32_t box[4] = {64, 1, 128, 1};
-    int rc = encode_tmap(&tm_qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, qkv, dims, strides, box,
+    uint32_t box_q[4] = {64, 1, uint32_t(kAtBM), 1};
+    int rc = encode_tmap(&tm_q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, qkv, dims, strides, box_q,
                          CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    uint32_t box_kv[4] = {64, 1, uint32_t(kAtBN), 1};
+    rc = encode_tmap(&tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
@@ -485,7 +498,7 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
-  int grid = p.num_items < sms ? p.num_items : sms;
+  int grid = p.num_items < 2 * sms ? p.num_items : 2 * sms;    // two CTAs per SM
   {
     // the opt-in to > 48 KB of dynamic shared memory is per device (nn.DataParallel drives several from one process)
     static bool attr_set[64] = {false};
@@ -493,11 +506,12 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
     MT_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
   MT_CHECK_CUDA(launch_pdl(attention_fwd_kernel, dim3(unsigned(grid)), dim3(kAtThreads), size_t(kAtSmemBytes),
-                           reinterpret_cast<cudaStream_t>(stream), 1u, tm_qkv, tm_out, p));
+                           reinterpret_cast<cudaStream_t>(stream), 1u, tm_q, tm_kv, tm_out, p));
   return MT_OK;
 }
 

@@ -59,6 +59,37 @@ assemble_tokens_kernel(const __nv_bfloat16* __restrict__ tok, const __nv_bfloat1
 }
 
 // ------------------------------------------------------------------------------------------------
+// embedding-bag sum: out[r, :] = pos[r % pos_period, :] + sum_f table[idx[r, f] + offs[f], :]
+// (calendar embeddings of the time-series tokenizer, Data2Seq/Time_Series.py:64-92; atom / bond feature embeddings of
+// the graph tokenizer, Data2Seq/Graph.py:254-255).  Gather-bound: one thread per (row, 4 columns), fp32 tables.
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+embed_sum_kernel(const float* __restrict__ table, const int* __restrict__ idx, const int* __restrict__ offs, int F,
+                 const float* __restrict__ pos, int pos_period, TOut* __restrict__ out, long long R, int d4) {
+  const long long total = R * d4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % d4);
+    const long long r = i / d4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos != nullptr) acc = reinterpret_cast<const float4*>(pos)[(r % pos_period) * d4 + c];
+    for (int f = 0; f < F; ++f) {
+      const long long row = (long long)idx[r * F + f] + (offs ? offs[f] : 0);
+      const float4 t = reinterpret_cast<const float4*>(table)[row * d4 + c];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if constexpr (sizeof(TOut) == 4) {
+      reinterpret_cast<float4*>(out)[i] = acc;
+    } else {
+      uint2 o;
+      o.x = pack_bf16x2(acc.x, acc.y);
+      o.y = pack_bf16x2(acc.z, acc.w);
+      reinterpret_cast<uint2*>(out)[i] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // final LayerNorm + pooling
 // ------------------------------------------------------------------------------------------------
 constexpr int kPoolThreads = 256;
@@ -371,6 +402,32 @@ extern "C" int mt_dropout(const void* x, const void* residual, const float* row_
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(residual), row_scale,
       rows_per_scale, reinterpret_cast<__nv_bfloat16*>(out), n8, d / 8, thresh, inv_keep,
       make_uint2(uint32_t(seed), uint32_t(seed >> 32)), offset);
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+extern "C" int mt_embed_sum(const float* table, const int* idx, const int* offsets, int F, const float* pos, int pos_period,
+                            void* out, int out_dtype, long long rows, int d, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(table && idx && out, MT_ERR_BAD_SHAPE, "mt_embed_sum: null pointer");
+  MT_REQUIRE(rows > 0 && F > 0 && d > 0 && d % 4 == 0, MT_ERR_BAD_SHAPE, "mt_embed_sum: need rows, F > 0 and d %% 4 == 0");
+  MT_REQUIRE(pos == nullptr || pos_period > 0, MT_ERR_BAD_SHAPE, "mt_embed_sum: pos needs pos_period > 0");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             MT_ERR_BAD_ALIGN, "mt_embed_sum: table / pos / out must be 16-byte aligned");
+  const long long total = rows * (d / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (out_dtype == MT_DT_F32)
+    embed_sum_kernel<float><<<unsigned(blocks), 256, 0, s>>>(table, idx, offsets, F, pos, pos_period,
+                                                             reinterpret_cast<float*>(out), rows, d / 4);
+  else if (out_dtype == MT_DT_BF16)
+    embed_sum_kernel<__nv_bfloat16><<<unsigned(blocks), 256, 0, s>>>(table, idx, offsets, F, pos, pos_period,
+                                                                     reinterpret_cast<__nv_bfloat16*>(out), rows, d / 4);
+  else {
+    set_error("mt_embed_sum: out_dtype must be bf16 or fp32");
+    return MT_ERR_BAD_DTYPE;
+  }
   MT_CHECK_CUDA(cudaGetLastError());
   return MT_OK;
 }

@@ -440,3 +440,21 @@ def pad_cols(x: torch.Tensor, width: int) -> torch.Tensor:
     with torch.cuda.device(x.device):
         check(_lib.load().mt_pad_cols(x.data_ptr(), out.data_ptr(), _DT[x.dtype], rows, c, width, _stream()), "mt_pad_cols")
     return out
+
+
+def embed_sum(table: torch.Tensor, idx: torch.Tensor, offsets: Optional[torch.Tensor] = None,
+              pos: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """Embedding-bag sum: out[r] = pos[r % len(pos)] + sum_f table[idx[r, f] + offsets[f]].  table fp32 [V,d], idx int32
+    [rows,F], offsets int32 [F] | None, pos fp32 [P,d] | None -> [rows, d] in out_dtype (bf16 / fp32)."""
+    _require_cuda(table, idx, offsets, pos)
+    if table.dtype != torch.float32 or idx.dtype != torch.int32 or (pos is not None and pos.dtype != torch.float32) \
+            or (offsets is not None and offsets.dtype != torch.int32):
+        raise ValueError("embed_sum: table / pos fp32, idx / offsets int32")
+    rows, F = idx.shape
+    d = table.shape[1]
+    out = torch.empty((rows, d), dtype=out_dtype, device=table.device)
+    with torch.cuda.device(table.device):
+        check(_lib.load().mt_embed_sum(table.data_ptr(), idx.data_ptr(), _ptr(offsets), F, _ptr(pos),
+                                       0 if pos is None else pos.shape[0], out.data_ptr(), _DT[out_dtype], rows, d, _stream()),
+              "mt_embed_sum")
+    return out

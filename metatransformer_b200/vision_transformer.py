@@ -36,8 +36,36 @@ class DropPath(nn.Module):
     def forward(self, x):
         if self.drop_prob == 0.0 or not self.training:
             return x
-        raise NotImplementedError("DropPath as a stand-alone module is not built; inside Block the stochastic depth is "
-                                  "fused with the residual add (mt_dropout)")
+        return _DropPathFn.apply(x, self.drop_prob)
+
+
+class _DropPathFn(torch.autograd.Function):
+    """Stand-alone stochastic depth: out = x * bernoulli(keep)[sample] / keep (timm.models.layers.drop_path), one pass of
+    the mt_dropout kernel with p = 0 and a per-sample row scale; the backward applies the same scale to the gradient.
+    (Inside Block the same kernel also performs the residual add.)"""
+
+    @staticmethod
+    def forward(ctx, x, drop_prob):
+        if not x.is_cuda:
+            raise RuntimeError("DropPath: CUDA (B200) tensors only; there is no CPU fallback")
+        keep = 1.0 - drop_prob
+        B = x.shape[0]
+        rs = torch.empty(B, dtype=torch.float32, device=x.device).bernoulli_(keep).div_(keep)
+        ctx.rs, ctx.rows_per = rs, x.numel() // B // x.shape[-1]
+        return _DropPathFn._scale(x, rs, ctx.rows_per)
+
+    @staticmethod
+    def _scale(t, rs, rows_per):
+        t2 = t.reshape(-1, t.shape[-1])
+        t2 = t2 if t2.is_contiguous() else t2.contiguous()
+        tb = t2 if t2.dtype == torch.bfloat16 else ops.cast(t2, torch.bfloat16)
+        out = ops.dropout(tb, 0.0, 0, 0, row_scale=rs, rows_per_scale=rows_per)
+        out = out if t.dtype == torch.bfloat16 else ops.cast(out, t.dtype)
+        return out.view(t.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _DropPathFn._scale(g, ctx.rs, ctx.rows_per), None
 
 
 def _philox_reserve(device: torch.device, n_elements: int):
@@ -385,7 +413,12 @@ class Block(nn.Module):
                                          f32(self.norm1.bias), dybq)
         return [dg1, dbt1, dwq, dybq if attn.qkv.bias is not None else None, dwp, dbp, dg2, dbt2, dw1, dyb1, dw2, db2]
 
-    def forward(self, x):
+    def forward(self, x, pos=None):
+        """`pos` (extension): a (1, N, C) / (N, C) table added to x before the Block — the PointCloud fork's
+        `x = block(x + pos_embed)` loop (PointCloud/openpoints/models/backbone/metatransformer.py:161-163) as one fused
+        pass instead of an eager add per layer; d pos = the batch sum of d x."""
+        if pos is not None:
+            x = _AddPosFn.apply(x, pos)
         _check_input(x, "Block")
         if self.training and self.attn.attn_drop.p > 0:
             raise NotImplementedError("Block: attn_drop > 0 in training mode is not implemented on the B200 path (the "
@@ -405,6 +438,36 @@ class Block(nn.Module):
         return _from_bf16(self._forward_2d(_to_bf16_2d(x), B, N)[0], x)
 
 
+class _AddPosFn(torch.autograd.Function):
+    """x (B, N, C) + pos (N, C) broadcast over the batch, one pass of mt_assemble_tokens (bf16 result)."""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        if not x.is_cuda:
+            raise RuntimeError("Block: CUDA (B200) tensors only; there is no CPU fallback")
+        B, N, C = x.shape
+        if pos.numel() != N * C:
+            raise ValueError(f"Block: pos must hold N*C = {N * C} values, got shape {tuple(pos.shape)}")
+        ctx.meta = (x.dtype, pos.dtype, pos.shape)
+        xb = _to_bf16_2d(x).view(B, N, C)
+        pb = pos.detach().reshape(N, C).contiguous()
+        pb = pb if pb.dtype == torch.bfloat16 else ops.cast(pb, torch.bfloat16)
+        return ops.assemble_tokens(xb, None, pb)
+
+    @staticmethod
+    def backward(ctx, g):
+        xdt, pdt, pshape = ctx.meta
+        B, N, C = g.shape
+        gb = g.contiguous()
+        gb = gb if gb.dtype == torch.bfloat16 else ops.cast(gb, torch.bfloat16)
+        dpos = None
+        if ctx.needs_input_grad[1]:
+            dpos = ops.colsum(gb.view(B, N * C)).view(pshape)
+            dpos = dpos if pdt == torch.float32 else ops.cast(dpos, pdt)
+        dx = g if g.dtype == xdt else ops.cast(gb, xdt)
+        return dx, dpos
+
+
 class _BlockFn(torch.autograd.Function):
     """Autograd node of one frozen Block: forward and input-gradient both run on the sm_100a kernels."""
 
@@ -418,6 +481,9 @@ class _BlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.saved is None:
+            raise RuntimeError("Block: backward through the same graph a second time is not supported (the saved "
+                               "activations are released after the first pass; retain_graph=True has no effect here)")
         B, N, C = ctx.shape
         g2 = _to_bf16_2d(g)
         dx2, inter = ctx.block._backward_2d(g2, ctx.saved, B, N)

@@ -155,6 +155,19 @@ def main():
     np.savez_compressed(OUT / "time_series_embed.npz", x=x.numpy(), y=y.numpy(),
                         w=de.value_embedding.tokenConv.weight.numpy())
     print("time_series_embed", tuple(y.shape))
+    # with calendar features: fixed sinusoid tables (freq 't': month, day, weekday, hour, minute) and the timeF Linear
+    g = torch.Generator().manual_seed(14)
+    de_f = ts_mod.DataEmbedding(c_in=7, d_model=64, embed_type='fixed', freq='t').eval()
+    xm = torch.stack([torch.randint(0, 13, (3, 96), generator=g), torch.randint(0, 32, (3, 96), generator=g),
+                      torch.randint(0, 7, (3, 96), generator=g), torch.randint(0, 24, (3, 96), generator=g),
+                      torch.randint(0, 4, (3, 96), generator=g)], dim=-1).float()
+    de_t = ts_mod.DataEmbedding(c_in=7, d_model=64, embed_type='timeF', freq='h').eval()
+    xt = torch.rand(3, 96, 4, generator=g) - 0.5
+    np.savez_compressed(OUT / "time_series_embed_mark.npz", x=x.numpy(), x_mark_fixed=xm.numpy(), y_fixed=de_f(x, xm).detach().numpy(),
+                        w_fixed=de_f.value_embedding.tokenConv.weight.detach().numpy(), x_mark_timef=xt.numpy(),
+                        y_timef=de_t(x, xt).detach().numpy(), w_timef=de_t.value_embedding.tokenConv.weight.detach().numpy(),
+                        w_timef_embed=de_t.temporal_embedding.embed.weight.detach().numpy())
+    print("time_series_embed_mark")
 
     # ---- AST tokenizer: the reference's PatchEmbed with the overlapping-stride conv ASTModel installs (:86) ----
     _stub_timm()

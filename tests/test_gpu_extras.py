@@ -287,3 +287,85 @@ def test_dropout_follows_torch_cuda_rng_and_checkpointing(mt):
     blk.attn.attn_drop.p = 0.1
     with pytest.raises(NotImplementedError):
         blk(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round-2 additions: calendar embeddings / training of the time-series tokenizer, stand-alone DropPath, Block(x, pos)
+# ---------------------------------------------------------------------------------------------------------------
+def test_time_series_calendar_embeddings_match_reference_golden(mt, golden_dir):
+    """DataEmbedding(x, x_mark) for the fixed sinusoid tables (freq 't': month/day/weekday/hour/minute) and the timeF
+    Linear, against vectors produced by the reference's own Data2Seq/Time_Series.py (tests/golden/make_golden.py)."""
+    import numpy as np
+    z = np.load(golden_dir / "time_series_embed_mark.npz")
+    x = torch.from_numpy(z["x"]).cuda()
+    emb = mt.data2seq.Time_Series.DataEmbedding(c_in=7, d_model=64, embed_type="fixed", freq="t")
+    emb.value_embedding.tokenConv.weight.data.copy_(torch.from_numpy(z["w_fixed"]))
+    emb = emb.cuda().eval()
+    with torch.no_grad():
+        y = emb(x, torch.from_numpy(z["x_mark_fixed"]).cuda())
+    _assert_close(y, torch.from_numpy(z["y_fixed"]), what="DataEmbedding + fixed calendar tables")
+    emb = mt.data2seq.Time_Series.DataEmbedding(c_in=7, d_model=64, embed_type="timeF", freq="h")
+    emb.value_embedding.tokenConv.weight.data.copy_(torch.from_numpy(z["w_timef"]))
+    emb.temporal_embedding.embed.weight.data.copy_(torch.from_numpy(z["w_timef_embed"]))
+    emb = emb.cuda().eval()
+    with torch.no_grad():
+        y = emb(x, torch.from_numpy(z["x_mark_timef"]).cuda())
+    _assert_close(y, torch.from_numpy(z["y_timef"]), what="DataEmbedding + timeF Linear")
+    # a reference state-dict loads strict (same sub-module names)
+    assert set(emb.state_dict().keys()) == {"value_embedding.tokenConv.weight", "position_embedding.pe",
+                                            "temporal_embedding.embed.weight"}
+
+
+def test_time_series_tokenizer_trains(mt):
+    """default construction (train mode, dropout 0.1) works out of the box; weight gradients vs fp64 autograd at p = 0"""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 48, 5, generator=g)
+    xt = torch.rand(2, 48, 4, generator=g) - 0.5
+    emb = mt.data2seq.Time_Series.DataEmbedding(c_in=5, d_model=96, embed_type="timeF", freq="h", dropout=0.0).cuda().train()
+    y = emb(x.cuda(), xt.cuda())
+    gy = torch.randn(2, 48, 96, generator=g)
+    y.backward(gy.cuda())
+    w = emb.value_embedding.tokenConv.weight.detach().cpu().double().requires_grad_(True)
+    wt = emb.temporal_embedding.embed.weight.detach().cpu().double().requires_grad_(True)
+    xp = x.double().permute(0, 2, 1)
+    ref = F.conv1d(F.pad(xp, (1, 1), mode="circular"), w).transpose(1, 2) + xt.double() @ wt.t() + \
+        orc.sinusoid_pe(48, 96).double()
+    ref.backward(gy.double())
+    _assert_close(y, ref.detach(), what="time-series tokens (train mode)")
+    _assert_close(emb.value_embedding.tokenConv.weight.grad, w.grad, rel=2e-2, mx=2e-2, what="dW conv1d")
+    _assert_close(emb.temporal_embedding.embed.weight.grad, wt.grad, rel=2e-2, mx=2e-2, what="dW timeF")
+    d2s = mt.Data2Seq("time-series", 64).cuda()            # default: train mode, dropout 0.1, trainable conv
+    out = d2s(torch.randn(2, 32, 1, device="cuda"))
+    out.float().sum().backward()
+    assert out.shape == (2, 32, 64) and d2s.embed.value_embedding.tokenConv.weight.grad is not None
+    zeros = (out == 0).float().mean().item()
+    assert 0.03 < zeros < 0.2, f"dropout(0.1) zeroed {zeros:.3f} of the tokens"
+
+
+def test_standalone_droppath_and_block_pos_prologue(mt):
+    g = torch.Generator().manual_seed(5)
+    dp = mt.vision_transformer.DropPath(0.4).cuda().train()
+    x = torch.randn(64, 10, 32, generator=g).cuda().requires_grad_(True)
+    y = dp(x)
+    scale = (y.detach() / x.detach()).mean(dim=(1, 2))
+    kept = (scale - 1 / 0.6).abs() < 2e-2
+    dropped = scale.abs() < 1e-6
+    assert bool((kept | dropped).all()) and 0.3 < kept.float().mean().item() < 0.9
+    y.sum().backward()
+    assert torch.allclose(x.grad[:, 0, 0], torch.where(kept, torch.tensor(1 / 0.6, device="cuda"), torch.tensor(0.0, device="cuda")),
+                          atol=2e-2)
+    assert dp.eval()(x) is x
+    # Block(x, pos) == Block(x + pos) (PointCloud fork's per-layer positional add)
+    sd = orc.make_encoder_state_dict(128, 1, seed=7)
+    blk = mt.Block(dim=128, num_heads=2, mlp_ratio=4., qkv_bias=True).cuda().eval()
+    blk.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+    xb = _bf16_round(torch.randn(3, 40, 128, generator=g))
+    pos = _bf16_round(torch.randn(1, 40, 128, generator=g) * 0.5)
+    ref = orc.block((xb + pos).double(), {k: v.double() for k, v in sd.items()}, "0.", 2)
+    with torch.no_grad():
+        got = blk(xb.cuda(), pos=pos.cuda())
+    _assert_close(got, ref, what="Block(x, pos)")
+    posp = pos.clone().cuda().requires_grad_(True)
+    out = blk(xb.cuda().requires_grad_(True), pos=posp)
+    out.float().sum().backward()
+    assert posp.grad is not None and posp.grad.shape == posp.shape and torch.isfinite(posp.grad).all()

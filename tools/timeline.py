@@ -42,52 +42,10 @@ def main():
     fused = mt.FusedEncoder(enc, use_cuda_graph=False)
     x = synthetic.make_tokens(B, N, dim, seed=1234).bfloat16().to(dev)
     y = torch.empty_like(x)
-    lib = _lib.load()
-    with torch.no_grad():
-        fused(x, out=y)                       # warm-up outside capture (function attributes, weight packing)
-        torch.cuda.synchronize()
-        cap = fused.launches_per_forward + 8
-        slots = torch.zeros(2 * cap, dtype=torch.int64, device=dev)
-        _lib.check(lib.mt_timeline_begin(slots.data_ptr(), cap), "mt_timeline_begin")
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            fused(x, out=y)
-        used = lib.mt_timeline_end()
-        for _ in range(args.settle):
-            g.replay()
-        torch.cuda.synchronize()
-        slots[0::2] = -1                      # 0xFFFF... for atomicMin
-        slots[1::2] = 0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        step_ms = e0.elapsed_time(e1)
-    t = slots.cpu().tolist()
-    names = ["center_split"]
-    for l in range(depth):
-        names += [f"L{l}.qkv", f"L{l}.attention", f"L{l}.proj", f"L{l}.fc1", f"L{l}.fc2"]
-    rows = []
-    t0 = min(t[2 * i] for i in range(used))
-    prev_end = None
-    for i in range(used):
-        s, e = t[2 * i] - t0, t[2 * i + 1] - t0
-        rows.append({"kernel": names[i] if i < len(names) else f"k{i}", "start_us": s / 1e3, "end_us": e / 1e3,
-                     "dur_us": (e - s) / 1e3, "gap_before_us": None if prev_end is None else (s - prev_end) / 1e3})
-        prev_end = e
-    total_us = max(r["end_us"] for r in rows)
-    kinds = {}
-    for r in rows:
-        k = r["kernel"].split(".")[-1]
-        kinds.setdefault(k, [0.0, 0])
-        kinds[k][0] += r["dur_us"]
-        kinds[k][1] += 1
-    gaps = [r["gap_before_us"] for r in rows if r["gap_before_us"] is not None]
-    summary = {"config": args.config, "B": B, "N": N, "kernels": used, "span_us": total_us, "event_step_ms": step_ms,
-               "sum_kernel_us": sum(r["dur_us"] for r in rows), "sum_gap_us": sum(gaps),
-               "mean_gap_us": sum(gaps) / max(len(gaps), 1), "max_gap_us": max(gaps) if gaps else 0.0,
-               "by_kind_us": {k: {"total": v[0], "launches": v[1], "mean": v[0] / v[1]} for k, v in kinds.items()}}
+    from metatransformer_b200 import timeline
+    res = timeline.record(fused, x, y, settle=args.settle)
+    rows, summary = res["rows"], res["summary"]
+    summary.update({"config": args.config, "B": B, "N": N})
     print(f"{'kernel':16s} {'start_us':>10s} {'dur_us':>9s} {'gap_us':>8s}")
     for r in rows[: 1 + 5 * 3] + rows[-5:]:
         gp = "" if r["gap_before_us"] is None else f"{r['gap_before_us']:8.2f}"
