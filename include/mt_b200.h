@@ -213,6 +213,13 @@ int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, 
 int mt_split_f32(const float* src, void* hi, void* lo, size_t n, void* stream);
 int mt_merge_f32(const void* hi, const void* lo, float* dst, size_t n, void* stream);
 
+/* ---- E8: gradient all-reduce for integrators that own an NCCL communicator ------------------------------------------
+ * In place: buf = scale * sum over ranks of buf (scale = 1 / world_size for DDP averaging,
+ * Video/run_class_finetuning.py:739-741).  `nccl_comm` is the caller's ncclComm_t; ncclAllReduce is resolved with dlopen
+ * at first use, so the library itself does not link NCCL.  The Python package drives the same collective through
+ * torch.distributed (metatransformer_b200/distributed.py: GradBucketReducer, overlapped with the backward).        */
+int mt_allreduce(void* nccl_comm, void* buf, size_t count, int dtype, float scale, void* stream);
+
 /* ---- device timeline (measurement aid, off by default) -----------------------------------------------------------
  * Between mt_timeline_begin and mt_timeline_end every instrumented launch (GEMM, attention forward, row statistics)
  * takes the next slot of `slots` (device memory, capacity x 2 x uint64): slot[0] = min over CTAs of %globaltimer at

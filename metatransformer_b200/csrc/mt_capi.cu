@@ -5,6 +5,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
+#include <dlfcn.h>
 
 namespace mt {
 
@@ -138,6 +139,16 @@ __global__ void merge_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __n
   }
 }
 
+// in-place scale of an all-reduced gradient bucket (the 1 / world_size of DDP's averaging)
+template <typename T>
+__global__ void scale_kernel(T* __restrict__ p, size_t n, float s) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if constexpr (sizeof(T) == 4) p[i] = p[i] * s;
+    else p[i] = __float2bfloat16_rn(__bfloat162float(p[i]) * s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // elementwise cast (weight packing fp32 -> bf16, boundary conversions). Memory-bound, 16 B per thread-load.
 // ------------------------------------------------------------------------------------------------
@@ -258,6 +269,40 @@ extern "C" int mt_merge_f32(const void* hi, const void* lo, float* dst, size_t n
   merge_f32_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(hi), reinterpret_cast<const __nv_bfloat16*>(lo), dst, n);
   MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+// ncclAllReduce through dlopen: libmt_b200.so has no link-time NCCL dependency (it must load on a box without NCCL for the
+// CPU-side symbol tests); the communicator belongs to the caller.
+extern "C" int mt_allreduce(void* nccl_comm, void* buf, size_t count, int dtype, float scale, void* stream) {
+  using namespace mt;
+  typedef int (*PFN_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  static PFN_ncclAllReduce fn = nullptr;
+  static bool tried = false;
+  MT_REQUIRE(nccl_comm && buf, MT_ERR_BAD_SHAPE, "mt_allreduce: null pointer");
+  MT_REQUIRE(dtype == MT_DT_F32 || dtype == MT_DT_BF16, MT_ERR_BAD_DTYPE, "mt_allreduce: dtype must be fp32 or bf16");
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) fn = reinterpret_cast<PFN_ncclAllReduce>(dlsym(h, "ncclAllReduce"));
+  }
+  MT_REQUIRE(fn != nullptr, MT_ERR_UNSUPPORTED, "mt_allreduce: libnccl.so.2 / ncclAllReduce not found");
+  if (count == 0) return MT_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int nccl_dt = (dtype == MT_DT_F32) ? 7 : 9;     // ncclFloat32, ncclBfloat16
+  const int rc = fn(buf, buf, count, nccl_dt, 0 /* ncclSum */, nccl_comm, s);
+  MT_REQUIRE(rc == 0, MT_ERR_CUDA, "mt_allreduce: ncclAllReduce failed with ncclResult %d", rc);
+  if (scale != 1.0f) {
+    int sms = 0;
+    int rc2 = sm_count(&sms);
+    if (rc2) return rc2;
+    size_t blocks = (count + 255) / 256;
+    if (blocks > size_t(sms) * 16) blocks = size_t(sms) * 16;
+    if (dtype == MT_DT_F32) scale_kernel<float><<<unsigned(blocks), 256, 0, s>>>(reinterpret_cast<float*>(buf), count, scale);
+    else scale_kernel<__nv_bfloat16><<<unsigned(blocks), 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(buf), count, scale);
+    MT_CHECK_CUDA(cudaGetLastError());
+  }
   return MT_OK;
 }
 

@@ -95,6 +95,10 @@ struct GemmParams {
   int mn_major;                 // 1: both operands are stored reduction-dim-major (A = dY[k, m], B = X[k, n]: the weight
                                 // gradient dW = dY^T X straight from the row-major activations, no transposed copies)
   unsigned long long* tl;       // optional timeline slot {first CTA start, last CTA end} in globaltimer ns, or nullptr
+  __nv_bfloat16* y_direct;      // != nullptr: the epilogue writes its bf16 results straight from registers (one 32-byte
+  __nv_bfloat16* ylo_direct;    // sector per thread and 16-column piece) instead of staging them in shared memory for a
+                                // TMA store: the staging write + TMA read of every tile competes with the operand
+                                // traffic of the main loop for the 128 B/clk of the shared-memory crossbar
 };
 
 // gelu(x) = x * Phi(x) with the exact (erf) definition, nn.GELU() default.
@@ -348,27 +352,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (do_ln && row < p.M) {
         float mean, rstd;
         if (p.ln_sums > 0) {
-          // Combine the per-slice shifted sums (Chan et al.): slice mean_i = shift_i + s1_i/n_i, M2_i = s2_i - s1_i^2/n_i,
-          // M2 = sum M2_i + n_i (mean_i - mean)^2.  Fixed order: deterministic.
+          // Combine the per-slice shifted sums in one streaming pass: every slice is re-referenced to the first slice's
+          // shift (d = shift_i - ref: S1 += s1_i + n_i d, S2 += s2_i + 2 d s1_i + n_i d^2), so the loads are independent
+          // of each other (unrolled: all in flight at once) and nothing cancels: ref is within a few sigma of the mean.
           const float4* ps = reinterpret_cast<const float4*>(p.row_stats) + size_t(row) * p.ln_sums;
-          const float ref = ps[0].x;
-          float acc_m = 0.f;
+          const float ref = __ldg(&ps[0].x);
+          float S1 = 0.f, S2 = 0.f;
+#pragma unroll 4
           for (int i = 0; i < p.ln_sums; ++i) {
-            const float4 r = ps[i];
+            const float4 r = __ldg(ps + i);
             const float n_i = float(min(64, p.K - 64 * i));
-            acc_m += fmaf(n_i, r.x - ref, r.y);
+            const float dd = r.x - ref;
+            S1 += fmaf(n_i, dd, r.y);
+            S2 += fmaf(dd, fmaf(n_i, dd, 2.0f * r.y), r.z);
           }
           const float inv_k = 1.0f / float(p.K);
-          mean = fmaf(acc_m, inv_k, ref);
-          float m2 = 0.f;
-          for (int i = 0; i < p.ln_sums; ++i) {
-            const float4 r = ps[i];
-            const float n_i = float(min(64, p.K - 64 * i));
-            const float inv_n = 1.0f / n_i;
-            const float dm = fmaf(r.y, inv_n, r.x) - mean;
-            m2 += fmaf(n_i * dm, dm, fmaf(-r.y * inv_n, r.y, r.z));
-          }
-          rstd = rsqrtf(fmaxf(m2 * inv_k, 0.f) + p.ln_eps);
+          const float m1 = S1 * inv_k;
+          mean = ref + m1;
+          rstd = rsqrtf(fmaxf(fmaf(S2, inv_k, -m1 * m1), 0.f) + p.ln_eps);
         } else {
           const float2 st = reinterpret_cast<const float2*>(p.row_stats)[row];
           mean = st.x;
@@ -450,15 +451,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         const uint32_t (&rhc)[8] = rh[piece & 1];
         const uint32_t (&rlc)[8] = rl[piece & 1];
-        if ((piece & 1) == 0 && store_pending) {
-          // staging buffer is about to be overwritten: the previous TMA store(s) must have read it
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-          store_pending = false;
-        }
+        uint32_t hp[8], lp[8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {       // one 16-byte staging chunk (8 columns) per step
-          uint32_t hp[4], lp[4];
+        for (int j = 0; j < 2; ++j) {       // one 16-byte chunk (8 columns) per step
 #pragma unroll
           for (int ii = 0; ii < 2; ++ii) {   // four columns per step
             const int i = 2 * j + ii;
@@ -508,25 +503,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             unpack_f32x2(v01, v0, v1);
             unpack_f32x2(v23, v2, v3);
             const uint32_t h01 = pack_bf16x2(v0, v1), h23 = pack_bf16x2(v2, v3);
-            hp[2 * ii + 0] = h01;
-            hp[2 * ii + 1] = h23;
+            hp[2 * i + 0] = h01;
+            hp[2 * i + 1] = h23;
             if constexpr (kHiLo) {
               // low half of the split representation: bf16(v - float(hi)); hi + lo carries 16 mantissa bits
               float l0, l1, l2, l3;
               unpack_f32x2(add_f32x2(v01, pack_f32x2(-bf16_lo(h01), -bf16_hi(h01))), l0, l1);
               unpack_f32x2(add_f32x2(v23, pack_f32x2(-bf16_lo(h23), -bf16_hi(h23))), l2, l3);
-              lp[2 * ii + 0] = pack_bf16x2(l0, l1);
-              lp[2 * ii + 1] = pack_bf16x2(l2, l3);
+              lp[2 * i + 0] = pack_bf16x2(l0, l1);
+              lp[2 * i + 1] = pack_bf16x2(l2, l3);
             }
           }
-          // 64B-swizzled store into the staging tile(s): row = lane, 32 bytes of this piece = chunks 2*(piece&1), +1
+        }
+        if (p.y_direct != nullptr) {
+          // one full 32-byte sector per thread: columns c_p .. c_p + 15 of this thread's row
+          if (row < p.M && c_p < p.N) {
+            __nv_bfloat16* dst = p.y_direct + size_t(row) * p.N + c_p;
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(hp[0]), "r"(hp[1]),
+                         "r"(hp[2]), "r"(hp[3]), "r"(hp[4]), "r"(hp[5]), "r"(hp[6]), "r"(hp[7]) : "memory");
+            if constexpr (kHiLo) {
+              if (p.ylo_direct != nullptr) {
+                __nv_bfloat16* dl = p.ylo_direct + size_t(row) * p.N + c_p;
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dl), "r"(lp[0]), "r"(lp[1]),
+                             "r"(lp[2]), "r"(lp[3]), "r"(lp[4]), "r"(lp[5]), "r"(lp[6]), "r"(lp[7]) : "memory");
+              }
+            }
+          }
+          continue;
+        }
+        if ((piece & 1) == 0 && store_pending) {
+          // staging buffer is about to be overwritten: the previous TMA store(s) must have read it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          store_pending = false;
+        }
+        // 64B-swizzled store into the staging tile(s): row = lane, 32 bytes of this piece = chunks 2*(piece&1), +1
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
           const uint32_t chunk = uint32_t((piece & 1) * 2 + j);
           const uint32_t addr = srow + ((chunk ^ swz) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]),
-                       "r"(hp[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[4 * j + 0]), "r"(hp[4 * j + 1]),
+                       "r"(hp[4 * j + 2]), "r"(hp[4 * j + 3]) : "memory");
           if constexpr (kHiLo) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048u), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]),
-                         "r"(lp[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048u), "r"(lp[4 * j + 0]),
+                         "r"(lp[4 * j + 1]), "r"(lp[4 * j + 2]), "r"(lp[4 * j + 3]) : "memory");
           }
         }
         if (piece & 1) {
@@ -643,6 +663,18 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   p.row_offset = c.row_offset;
   p.out_f32 = c.out_f32;
   p.tl = timeline_next_slot();
+  {
+    // MT_B200_EPI_DIRECT: 1 = every bf16 output leaves the epilogue as 32-byte register stores, 0 = staged + TMA store
+    static int direct = -1;
+    if (direct < 0) {
+      const char* e = getenv("MT_B200_EPI_DIRECT");
+      direct = (e && e[0] == '1') ? 1 : 0;
+    }
+    const bool ok = direct && c.out_f32 == nullptr && (reinterpret_cast<uintptr_t>(c.y) & 31) == 0 &&
+                    (reinterpret_cast<uintptr_t>(c.y_lo) & 31) == 0 && (N % 16) == 0;
+    p.y_direct = ok ? reinterpret_cast<__nv_bfloat16*>(c.y) : nullptr;
+    p.ylo_direct = ok ? reinterpret_cast<__nv_bfloat16*>(c.y_lo) : nullptr;
+  }
   {
     const int num_kb = ceil_div(K, kBK);
     int sk = c.split_k < 1 ? 1 : (c.split_k > num_kb ? num_kb : c.split_k);

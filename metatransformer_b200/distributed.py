@@ -75,6 +75,100 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], world: int, bucket
     return n_coll
 
 
+class GradBucketReducer:
+    """Bucketed, overlapped gradient all-reduce for the fine-tune / trainable-tokenizer steps (DDP semantics of
+    Video/run_class_finetuning.py:739-741, without wrapping the model).
+
+    * Persistent flat buckets: every trainable parameter's `.grad` is a VIEW into one of a few flat fp32 (or bf16) buffers,
+      filled in reverse registration order (= the order backward produces them), so a bucket is reduced in place — no
+      torch.cat, no copy-back.
+    * A post-accumulate hook per parameter counts arrivals; when the last gradient of a bucket has been written the bucket's
+      all-reduce is issued asynchronously (NCCL runs it on its own stream after an event on the compute stream), i.e. while
+      the backward of the earlier Blocks is still running.  `finish()` waits for the outstanding collectives and divides by
+      the world size.  Between steps call `zero()` (or zero the grads in place); never set `.grad = None`.
+    Buckets are sized for launch latency and overlap (NVSwitch gives every peer full bandwidth; there is no per-link
+    sizing to do): one bucket per ~`bucket_bytes` of gradients, a single bucket for the 0.8-6 MB frozen-encoder cases.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], world: int, bucket_bytes: int = 64 << 20, group=None,
+                 grad_dtype: Optional[torch.dtype] = None):
+        self.world, self.group = world, group
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets: List[torch.Tensor] = []
+        self._bucket_of = {}
+        self._pending: List[int] = []
+        self._expected: List[int] = []
+        self._works = []
+        self._hooks = []
+        self.collectives_issued = 0
+        cur: List[torch.nn.Parameter] = []
+        size = 0
+        groups: List[List[torch.nn.Parameter]] = []
+        for p in reversed(self.params):
+            nbytes = p.numel() * (torch.empty((), dtype=grad_dtype or p.dtype).element_size())
+            if cur and (size + nbytes > bucket_bytes or (grad_dtype or p.dtype) != (grad_dtype or cur[0].dtype)
+                        or p.device != cur[0].device):
+                groups.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            groups.append(cur)
+        for bi, grp in enumerate(groups):
+            dt = grad_dtype or grp[0].dtype
+            flat = torch.zeros(sum(p.numel() for p in grp), dtype=dt, device=grp[0].device)
+            off = 0
+            for p in grp:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._bucket_of[p] = bi
+            self.buckets.append(flat)
+            self._expected.append(len(grp))
+            self._pending.append(len(grp))
+        if world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        bi = self._bucket_of[p]
+        flat = self.buckets[bi]
+        if p.grad.data_ptr() < flat.data_ptr() or p.grad.data_ptr() >= flat.data_ptr() + flat.numel() * flat.element_size():
+            raise RuntimeError("GradBucketReducer: a parameter's .grad was replaced (set to None / reassigned); zero the "
+                               "gradients in place (reducer.zero()) so that they stay views of the flat buckets")
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self.collectives_issued += 1
+
+    def finish(self) -> int:
+        """Wait for this step's collectives, average, re-arm for the next step.  Returns the number of collectives.
+        Buckets whose gradients did not all arrive (unused parameters) are reduced here, after the backward."""
+        n = 0
+        if self.world > 1:
+            for bi, left in enumerate(self._pending):
+                if left != 0:
+                    self._works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, group=self.group,
+                                                       async_op=True))
+                    self.collectives_issued += 1
+            for w in self._works:
+                w.wait()
+            n = len(self._works)
+            for flat in self.buckets:
+                flat.div_(self.world)
+        self._works = []
+        self._pending = list(self._expected)
+        return n
+
+    def zero(self) -> None:
+        for flat in self.buckets:
+            flat.zero_()
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def max_over_ranks(value: float, device: torch.device, world: int) -> float:
     if world <= 1:
         return value

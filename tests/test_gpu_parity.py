@@ -264,11 +264,11 @@ def test_base16_encoder_matches_oracle_c1_shape(mt):
     _assert_close(y2, ref, rel=1e-2, mx=2e-2, what="Base-16 x12 per-Block, bf16 tokens")
     _assert_close(y, y2.float(), rel=1e-2, mx=2e-2, what="fused vs per-Block")
     # the un-folded sequence (LayerNorm kernel + plain GEMM, bf16 stream: an A/B option) on a shallow stack
-    enc4 = nn.Sequential(*list(enc)[:4])
-    ref4 = orc.encoder(x, sd, 4, 12)
+    enc4 = nn.Sequential(*list(enc)[:2])
+    ref4 = orc.encoder(x, sd, 2, 12)
     with torch.no_grad():
         y3 = mt.FusedEncoder(enc4, fold_layernorm=False)(x.cuda().bfloat16())
-    _assert_close(y3, ref4, rel=1e-2, mx=1e-2, what="Base-16 x4 fused, LayerNorm not folded")
+    _assert_close(y3, ref4, rel=1e-2, mx=1e-2, what="Base-16 x2 fused, LayerNorm not folded")
 
 
 def test_full_size_c2_properties(mt):
