@@ -149,6 +149,18 @@ int mt_attention_bwd_workspace_bytes(int B, int N, int H, size_t* bytes);
 int mt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
                      void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale, void* stream);
 
+/* Training forms with attention dropout (timm Attention.attn_drop, attention.py:33; the Graph fork trains with
+ * attn_drop = 0.1, Graph/metatransformer/modules/tokengt_graph_encoder.py:200): attn = softmax(..); attn = keep * attn /
+ * (1 - drop_p); out = attn @ v.  keep(b, h, q, k) is a hash of (seed, b*H + h, q*N + k) evaluated inside the kernels —
+ * nothing is stored; the backward and mt_attention_dropout_mask (uint8 [B,H,N,N], test aid) replay it.  dh = 64 only
+ * (smaller heads are zero-padded to 64 lanes by the host modules).  lse2 may be NULL in the forward.              */
+int mt_attention_fwd_ex(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale, float drop_p,
+                        unsigned long long seed, void* stream);
+int mt_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                        void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale, float drop_p,
+                        unsigned long long seed, void* stream);
+int mt_attention_dropout_mask(void* mask, int B, int N, int H, float drop_p, unsigned long long seed, void* stream);
+
 /* ---- T1/T2/T3: patch / spectrogram / tubelet embedding -----------------------------------------------------
  * Non-overlapping or strided Conv{2,3}d as im2row + GEMM.
  * mt_im2row: x [B, C, T, H, W] (x_dtype fp32 or bf16; T = kt = 1 for 2-D) -> rows bf16 [B*Tp*Hp*Wp, C*kt*kh*kw]

@@ -22,7 +22,8 @@ EXPORTED_SYMBOLS = (
     "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_assemble_tokens", "mt_pool_layernorm", "mt_pool_layernorm_bwd",
     "mt_dropout", "mt_pad_cols", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
     "mt_encoder_forward", "mt_encoder_forward_ex", "mt_encoder_launches_per_forward",
-    "mt_row_stats_split", "mt_center_split", "mt_embed_sum", "mt_split_f32", "mt_merge_f32", "mt_timeline_begin", "mt_timeline_end", "mt_allreduce",
+    "mt_row_stats_split", "mt_center_split", "mt_embed_sum", "mt_split_f32", "mt_merge_f32", "mt_timeline_begin", "mt_timeline_end", "mt_allreduce", "mt_attention_fwd_ex", "mt_attention_bwd_ex",
+    "mt_attention_dropout_mask",
 )
 
 
@@ -140,6 +141,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_split_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.mt_merge_f32.restype = c_int
     lib.mt_merge_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.mt_attention_fwd_ex.restype = c_int
+    lib.mt_attention_fwd_ex.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                        c_ulonglong, c_void_p]
+    lib.mt_attention_bwd_ex.restype = c_int
+    lib.mt_attention_bwd_ex.argtypes = [c_void_p] * 6 + [c_size_t, c_int, c_int, c_int, c_int, c_float, c_float, c_ulonglong,
+                                                         c_void_p]
+    lib.mt_attention_dropout_mask.restype = c_int
+    lib.mt_attention_dropout_mask.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_ulonglong, c_void_p]
     lib.mt_allreduce.restype = c_int
     lib.mt_allreduce.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_float, c_void_p]
     lib.mt_timeline_begin.restype = c_int

@@ -66,6 +66,11 @@ struct AttnParams {
   float scale_log2;  // scale * log2(e)
   float* lse2;       // optional [B, H, N]: log2-sum-exp of the scaled scores (m*c + log2 l), saved for the backward
   unsigned long long* tl;   // optional timeline slot (mt_timeline_begin)
+  // attention dropout (training, Graph fork): P is multiplied by keep(q, k) before P.V and O by 1 / (1 - p); the row sum
+  // l stays the sum of the undropped probabilities (softmax first, dropout second: attention.py:32-33)
+  uint32_t drop_thresh;     // p * 2^32, 0 = no dropout
+  float drop_scale;         // 1 / (1 - p)
+  uint32_t seed_lo, seed_hi;
 };
 
 __global__ void __launch_bounds__(kAtThreads, 2)
@@ -277,6 +282,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       float m_run = -INFINITY;
       float l_run = 0.f;
+      const uint32_t bh_seed = attn_drop_seed(p.seed_lo, p.seed_hi, uint32_t(bh));
+      const uint32_t drop_row = uint32_t(qp * 256 + t * 128 + r_in_tile) * uint32_t(p.N);   // q * N
 
       for (int j = 0; j < p.num_kv; ++j) {
         const int valid = min(kAtBN, p.N - j * kAtBN);
@@ -375,9 +382,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 float a0, a1;
                 unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sq[8 * g + 2 * i]), __uint_as_float(sq[8 * g + 2 * i + 1])),
                                        c2, nmc2), a0, a1);
-                const float e0 = ex2_approx(a0);
-                const float e1 = ex2_approx(a1);
+                float e0 = ex2_approx(a0);
+                float e1 = ex2_approx(a1);
                 l2 = add_f32x2(l2, pack_f32x2(e0, e1));
+                if (p.drop_thresh != 0u) {
+                  const uint32_t kidx = drop_row + uint32_t(j * kAtBN + 16 * qi + 8 * g + 2 * i);
+                  if (!attn_keep(bh_seed, kidx, p.drop_thresh)) e0 = 0.f;
+                  if (!attn_keep(bh_seed, kidx + 1u, p.drop_thresh)) e1 = 0.f;
+                }
                 pk[i] = pack_bf16x2(e0, e1);
               }
               const uint32_t chunk16 = uint32_t(2 * qi + g);
@@ -401,7 +413,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_wait(o_done(t), n_od & 1u);
       ++n_od;
       tc_fence_after();
-      const float inv_l = 1.0f / l_run;
+      const float inv_l = p.drop_scale / l_run;
       const uint64_t inv_l2 = pack_f32x2(inv_l, inv_l);
       {
         const int qrow = qp * 256 + t * 128 + r_in_tile;
@@ -454,10 +466,12 @@ int attention_generic_fwd(const void* qkv, void* out, int B, int N, int H, int d
 }
 
 static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale,
-                              void* stream) {
+                              void* stream, float drop_p = 0.f, unsigned long long seed = 0ull) {
   using namespace mt;
   MT_REQUIRE(qkv && out, MT_ERR_BAD_SHAPE, "mt_attention_fwd: null pointer");
-  if (dh != 64 && lse2 == nullptr && B > 0 && N > 0 && H > 0 && scale > 0.f &&
+  MT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MT_ERR_BAD_SHAPE, "mt_attention_fwd: drop_p must be in [0, 1)");
+  MT_REQUIRE(drop_p == 0.f || (long long)N * N < (1ll << 32), MT_ERR_UNSUPPORTED, "mt_attention_fwd: dropout needs N < 65536");
+  if (dh != 64 && lse2 == nullptr && drop_p == 0.f && B > 0 && N > 0 && H > 0 && scale > 0.f &&
       ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
     return attention_generic_fwd(qkv, out, B, N, H, dh, scale, reinterpret_cast<cudaStream_t>(stream));
   MT_REQUIRE(B > 0 && N > 0 && H > 0, MT_ERR_BAD_SHAPE, "mt_attention_fwd: B, N, H must be positive");
@@ -495,6 +509,10 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse2 = lse2;
   p.tl = timeline_next_slot();
+  p.drop_thresh = drop_p > 0.f ? uint32_t(double(drop_p) * 4294967296.0) : 0u;
+  p.drop_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  p.seed_lo = uint32_t(seed);
+  p.seed_hi = uint32_t(seed >> 32);
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;
@@ -526,4 +544,35 @@ extern "C" int mt_attention_fwd_lse(const void* qkv, void* out, float* lse2, int
     return MT_ERR_BAD_SHAPE;
   }
   return attention_fwd_impl(qkv, out, lse2, B, N, H, dh, scale, stream);
+}
+
+// training forward with attention dropout (attn_drop > 0: Graph/metatransformer/modules/tokengt_graph_encoder.py:200):
+// softmax, then Bernoulli(1 - drop_p) keep mask scaled by 1 / (1 - drop_p), then .V; the mask is a pure function of
+// (seed, batch, head, query, key) that mt_attention_bwd_ex and mt_attention_dropout_mask replay.
+extern "C" int mt_attention_fwd_ex(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale,
+                                   float drop_p, unsigned long long seed, void* stream) {
+  return attention_fwd_impl(qkv, out, lse2, B, N, H, dh, scale, stream, drop_p, seed);
+}
+
+namespace mt {
+__global__ void attn_dropout_mask_kernel(uint8_t* __restrict__ mask, int BH, int N, uint32_t thresh, uint32_t seed_lo,
+                                         uint32_t seed_hi) {
+  const long long total = (long long)BH * N * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t bh = uint32_t(i / ((long long)N * N));
+    const uint32_t idx = uint32_t(i % ((long long)N * N));
+    mask[i] = attn_keep(attn_drop_seed(seed_lo, seed_hi, bh), idx, thresh) ? 1 : 0;
+  }
+}
+}  // namespace mt
+
+// the keep mask [B, H, N, N] (uint8) the attention kernels apply for (drop_p, seed): test / debugging aid
+extern "C" int mt_attention_dropout_mask(void* mask, int B, int N, int H, float drop_p, unsigned long long seed, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(mask && B > 0 && N > 0 && H > 0 && drop_p > 0.f && drop_p < 1.f, MT_ERR_BAD_SHAPE,
+             "mt_attention_dropout_mask: bad arguments");
+  attn_dropout_mask_kernel<<<1184, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint8_t*>(mask), B * H, N, uint32_t(double(drop_p) * 4294967296.0), uint32_t(seed), uint32_t(seed >> 32));
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
 }

@@ -62,6 +62,11 @@ struct AttnBwdParams {
   const float* delta;    // [B, H, N]
   float* dq_acc;         // [B, N, H, 64] fp32 zero-filled accumulator (unused in resident mode)
   __nv_bfloat16* dqkv;   // [B, N, 3, H, 64]
+  // attention dropout of the forward (mt_attention_fwd_ex), replayed from the same hash: A = P * keep / (1 - p) feeds dV,
+  // dS = P * (keep / (1 - p) * dP - delta) * scale (delta = rowsum(dO * O) already contains the dropped probabilities)
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint32_t seed_lo, seed_hi;
 };
 
 // 32-byte store of 16 bf16 values held as fp32 bit patterns in o[0..15] (full-sector writes from scattered rows)
@@ -393,6 +398,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     for (; cur.valid; ++n_pair) {
       const AbPair nxt = ab_next(cur, p, NT);
       const bool key_ok = (cur.j * 128 + r) < p.N;
+      const uint32_t bh_seed = attn_drop_seed(p.seed_lo, p.seed_hi, uint32_t(ab_bh(cur, p, NT)));
+      const uint32_t key_idx = uint32_t(cur.j * 128 + r);
       float* st_l = stat + (n_pair & 1u) * 256;
       if (hf == 0) {
         st_l[r] = pf_l;
@@ -423,8 +430,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           float p0 = ex2f(fmaf(__uint_as_float(s[c0]), c, -l2.x));
           float p1 = ex2f(fmaf(__uint_as_float(s[c0 + 1]), c, -l2.y));
           if (!key_ok) { p0 = 0.f; p1 = 0.f; }
-          const float d0 = p0 * (__uint_as_float(dp[c0]) - dl.x) * sc;
-          const float d1 = p1 * (__uint_as_float(dp[c0 + 1]) - dl.y) * sc;
+          float m0 = 1.f, m1 = 1.f;
+          if (p.drop_thresh != 0u) {
+            const uint32_t qidx = uint32_t(cur.i * 128 + 64 * hf + 32 * sub + c0) * uint32_t(p.N) + key_idx;
+            m0 = attn_keep(bh_seed, qidx, p.drop_thresh) ? p.drop_scale : 0.f;
+            m1 = attn_keep(bh_seed, qidx + uint32_t(p.N), p.drop_thresh) ? p.drop_scale : 0.f;
+          }
+          const float d0 = p0 * fmaf(__uint_as_float(dp[c0]), m0, -dl.x) * sc;
+          const float d1 = p1 * fmaf(__uint_as_float(dp[c0 + 1]), m1, -dl.y) * sc;
+          p0 *= m0;
+          p1 *= m1;
           pp[sub][e] = pack_bf16x2(p0, p1);
           dd[sub][e] = pack_bf16x2(d0, d1);
         }
@@ -482,10 +497,12 @@ extern "C" int mt_attention_bwd_workspace_bytes(int B, int N, int H, size_t* byt
   return MT_OK;
 }
 
-extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
-                                void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale,
-                                void* stream) {
+static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                              void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale,
+                              float drop_p, unsigned long long seed, void* stream) {
   using namespace mt;
+  MT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MT_ERR_BAD_SHAPE, "mt_attention_bwd: drop_p must be in [0, 1)");
+  MT_REQUIRE(drop_p == 0.f || (long long)N * N < (1ll << 32), MT_ERR_UNSUPPORTED, "mt_attention_bwd: dropout needs N < 65536");
   MT_REQUIRE(qkv && out && dout && lse2 && dqkv && workspace, MT_ERR_BAD_SHAPE, "mt_attention_bwd: null pointer");
   MT_REQUIRE(B > 0 && N > 0 && H > 0, MT_ERR_BAD_SHAPE, "mt_attention_bwd: B, N, H must be positive");
   MT_REQUIRE(dh == 64, MT_ERR_UNSUPPORTED, "mt_attention_bwd: head_dim %d not supported (only 64)", dh);
@@ -549,6 +566,10 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
   p.delta = delta;
   p.dq_acc = dq_acc;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.drop_thresh = drop_p > 0.f ? uint32_t(double(drop_p) * 4294967296.0) : 0u;
+  p.drop_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  p.seed_lo = uint32_t(seed);
+  p.seed_hi = uint32_t(seed >> 32);
   const int grid = p.num_work < sms ? p.num_work : sms;
   {
     // the opt-in to > 48 KB of dynamic shared memory is per device (nn.DataParallel drives several from one process)
@@ -579,4 +600,17 @@ extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* do
     MT_CHECK_CUDA(cudaGetLastError());
   }
   return MT_OK;
+}
+
+extern "C" int mt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                                void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale,
+                                void* stream) {
+  return attention_bwd_impl(qkv, out, dout, lse2, dqkv, workspace, workspace_bytes, B, N, H, dh, scale, 0.f, 0ull, stream);
+}
+
+// backward of mt_attention_fwd_ex: same (drop_p, seed) => same keep mask
+extern "C" int mt_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse2, void* dqkv,
+                                   void* workspace, size_t workspace_bytes, int B, int N, int H, int dh, float scale,
+                                   float drop_p, unsigned long long seed, void* stream) {
+  return attention_bwd_impl(qkv, out, dout, lse2, dqkv, workspace, workspace_bytes, B, N, H, dh, scale, drop_p, seed, stream);
 }

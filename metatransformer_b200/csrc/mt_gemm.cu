@@ -22,6 +22,8 @@
 //
 // Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
 // warps 4..19 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the 64-column quarter of the tile).
+// a timed-out barrier wait traps without the device printf (the call sequence costs registers in every role)
+#define MT_WAIT_QUIET 1
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 #include <stdlib.h>
@@ -56,8 +58,10 @@ struct GemmCfg {
   static constexpr int kBRows = (CG == 2) ? kBN / 2 : kBN;            // rows of W this CTA loads
   static constexpr int kBBytes = kBRows * kBK * 2;                    // 16 / 32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CG == 2) ? (HILO ? 4 : 5) : 3;
-  static constexpr int kEpiStageBytes = HILO ? 4096 : 2048;           // per warp: 32 rows x 32 columns bf16 (hi [, lo])
+  static constexpr int kStages = (CG == 2) ? 5 : 3;
+  // per warp: 32 rows x 32 columns bf16 (one 2 KB TMA store per 32-column slice), or — split stream — 32 rows x 16
+  // columns of hi + the same of lo (two 1 KB stores per 16-column piece)
+  static constexpr int kEpiStageBytes = 2048;
   static constexpr int kSmemEpiOff = kStages * kStageBytes;
   static constexpr int kSmemBiasOff = kSmemEpiOff + kEpiWarps * kEpiStageBytes;
   static constexpr int kSmemBarOff = kSmemBiasOff + kEpiWarps * kBiasBytes;
@@ -217,6 +221,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;   // work items: (tile, K split), split fastest
   const int num_kb = (p.K + kBK - 1) / kBK;
 
+  // register re-distribution (compiled for 96 / thread): the four role warps need almost nothing, the residual epilogue
+  // holds a whole tile's worth of prefetched residual (hi) per thread
+  if (warp < kRoleWarps) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -310,8 +318,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (++as == kAccStages) { as = 0; aphase ^= 1u; }
       }
     }
-  } else if (warp >= kRoleWarps) {
+  }
+  } else {
     // =============================== epilogue ===================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // 16 warps: warp % 4 = TMEM lane quarter (32 output rows), (warp - 4) / 4 = 64-column quarter of the 256-wide tile.
     // Per tile and warp: four 16-column pieces (tcgen05.ld x16 -> math -> bf16 -> 64B-swizzled staging), two TMA stores
     // of 32 rows x 32 columns.  Everything a piece needs from global memory (residual) is fetched one piece ahead.
@@ -327,8 +337,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int cq = ew >> 2;
     const uint32_t stg = smem_base + Cfg::kSmemEpiOff + ew * Cfg::kEpiStageBytes;
     const float4* bias_s4 = reinterpret_cast<const float4*>(smem_gen + Cfg::kSmemBiasOff + ew * kBiasBytes);
-    const uint32_t srow = stg + uint32_t(lane * 64);
-    const uint32_t swz = uint32_t(lane >> 1) & 3u;     // 64B swizzle: 16-byte chunk index ^ ((row >> 1) & 3)
+    // staging layouts: 64-byte rows with the 64B swizzle (chunk ^ ((row >> 1) & 3)); split stream: 32-byte rows with
+    // the 32B swizzle (chunk ^ ((row >> 2) & 1)), hi at +0, lo at +1024
+    const uint32_t srow = stg + uint32_t(lane * (kHiLo ? 32 : 64));
+    const uint32_t swz = kHiLo ? (uint32_t(lane >> 2) & 1u) : (uint32_t(lane >> 1) & 3u);
     int as = 0;
     uint32_t aphase = 0;
     bool store_pending = false;
@@ -399,23 +411,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         rrow = p.resid + rr;
         if (kHiLo && p.resid_lo != nullptr) rrow_lo = p.resid_lo + rr;
       }
-      uint32_t rh[2][8], rl[2][8];
-      auto load_resid = [&](int piece, uint32_t (&h)[8], uint32_t (&l)[8]) {
+      // kEpiRes: the hi halves of all four pieces are requested up front (64 KB per SM in flight while the main loop of
+      // this tile still runs), the lo halves one piece ahead; generic mode: one piece ahead
+      constexpr int kRhBufs = kHiLo ? (kEpiCols / kPiece) : 2;
+      uint32_t rh[kRhBufs][8], rl[2][8];
+      auto load_hi = [&](int piece, uint32_t (&h)[8]) {
         const int c_ = col0 + kPiece * piece;
         if (rrow != nullptr && c_ < p.N) ldg_nc_v8(rrow + c_, h);
         else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) h[j] = 0u;
         }
-        if constexpr (kHiLo) {
-          if (rrow_lo != nullptr && c_ < p.N) ldg_nc_v8(rrow_lo + c_, l);
-          else {
+      };
+      auto load_lo = [&](int piece, uint32_t (&l)[8]) {
+        const int c_ = col0 + kPiece * piece;
+        if (rrow_lo != nullptr && c_ < p.N) ldg_nc_v8(rrow_lo + c_, l);
+        else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) l[j] = 0u;
-          }
+          for (int j = 0; j < 8; ++j) l[j] = 0u;
         }
       };
-      if (do_resid) load_resid(0, rh[0], rl[0]);
+      if (do_resid) {
+        if constexpr (kHiLo) {
+#pragma unroll
+          for (int pc = 0; pc < kEpiCols / kPiece; ++pc) load_hi(pc, rh[pc]);
+          load_lo(0, rl[0]);
+        } else {
+          load_hi(0, rh[0]);
+        }
+      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(32 * q) << 16) + uint32_t(as * kBN + kEpiCols * cq);
@@ -424,7 +448,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int c_p = col0 + kPiece * piece;
         uint32_t acc[16];
         tmem_ld_32x32b_x16(t_row + uint32_t(kPiece * piece), acc);
-        if (do_resid && piece + 1 < kEpiCols / kPiece) load_resid(piece + 1, rh[(piece + 1) & 1], rl[(piece + 1) & 1]);
+        if (do_resid && piece + 1 < kEpiCols / kPiece) {
+          if constexpr (kHiLo) load_lo(piece + 1, rl[(piece + 1) & 1]);
+          else load_hi(piece + 1, rh[(piece + 1) & 1]);
+        }
         tmem_wait_ld();
         if (piece == kEpiCols / kPiece - 1) {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA issuer
@@ -449,7 +476,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           continue;
         }
-        const uint32_t (&rhc)[8] = rh[piece & 1];
+        const uint32_t (&rhc)[8] = rh[kHiLo ? piece : (piece & 1)];
         const uint32_t (&rlc)[8] = rl[piece & 1];
         uint32_t hp[8], lp[8];
 #pragma unroll
@@ -531,35 +558,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           continue;
         }
-        if ((piece & 1) == 0 && store_pending) {
-          // staging buffer is about to be overwritten: the previous TMA store(s) must have read it
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-          store_pending = false;
-        }
-        // 64B-swizzled store into the staging tile(s): row = lane, 32 bytes of this piece = chunks 2*(piece&1), +1
+        if constexpr (kHiLo) {
+          // split stream: one 32-row x 16-column box of hi and one of lo per piece
+          if (store_pending) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            store_pending = false;
+          }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint32_t chunk = uint32_t((piece & 1) * 2 + j);
-          const uint32_t addr = srow + ((chunk ^ swz) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[4 * j + 0]), "r"(hp[4 * j + 1]),
-                       "r"(hp[4 * j + 2]), "r"(hp[4 * j + 3]) : "memory");
-          if constexpr (kHiLo) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048u), "r"(lp[4 * j + 0]),
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t addr = srow + ((uint32_t(j) ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[4 * j + 0]), "r"(hp[4 * j + 1]),
+                         "r"(hp[4 * j + 2]), "r"(hp[4 * j + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 1024u), "r"(lp[4 * j + 0]),
                          "r"(lp[4 * j + 1]), "r"(lp[4 * j + 2]), "r"(lp[4 * j + 3]) : "memory");
           }
-        }
-        if (piece & 1) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && (c_p - kPiece) < p.N) {
-            tma_store_2d(&tm_y, stg, c_p - kPiece, row0);
-            if constexpr (kHiLo) {
-              if (p.has_out_lo) tma_store_2d(&tm_ylo, stg + 2048u, c_p - kPiece, row0);
-            }
+          if (lane == 0 && row0 < p.M && c_p < p.N) {
+            tma_store_2d(&tm_y, stg, c_p, row0);
+            if (p.has_out_lo) tma_store_2d(&tm_ylo, stg + 1024u, c_p, row0);
             tma_store_commit();
           }
           store_pending = true;
+        } else {
+          if ((piece & 1) == 0 && store_pending) {
+            // staging buffer is about to be overwritten: the previous TMA store must have read it
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            store_pending = false;
+          }
+          // 64B-swizzled store into the staging tile: row = lane, 32 bytes of this piece = chunks 2*(piece&1), +1
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t chunk = uint32_t((piece & 1) * 2 + j);
+            const uint32_t addr = srow + ((chunk ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[4 * j + 0]), "r"(hp[4 * j + 1]),
+                         "r"(hp[4 * j + 2]), "r"(hp[4 * j + 3]) : "memory");
+          }
+          if (piece & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M && (c_p - kPiece) < p.N) {
+              tma_store_2d(&tm_y, stg, c_p - kPiece, row0);
+              tma_store_commit();
+            }
+            store_pending = true;
+          }
         }
       }
       if (do_sums && row < p.M && col0 < p.N) {
@@ -637,12 +682,12 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     const uint64_t outer = c.out_f32 ? uint64_t(c.mn_major ? K : M) : uint64_t(M);
     uint64_t dims[2] = {inner, outer};
     uint64_t strides[1] = {inner * 2};
-    uint32_t box[2] = {32u, 32u};
-    int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.out_f32 ? c.x : c.y, dims, strides, box,
-                         CU_TENSOR_MAP_SWIZZLE_64B);
+    uint32_t box[2] = {kHiLo ? 16u : 32u, 32u};
+    const CUtensorMapSwizzle sw = kHiLo ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+    int rc = encode_tmap(&tm_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.out_f32 ? c.x : c.y, dims, strides, box, sw);
     if (rc) return rc;
     rc = encode_tmap(&tm_ylo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.out_f32 ? c.x : (c.y_lo ? c.y_lo : c.y), dims, strides,
-                     box, CU_TENSOR_MAP_SWIZZLE_64B);
+                     box, sw);
     if (rc) return rc;
   }
   GemmParams p;

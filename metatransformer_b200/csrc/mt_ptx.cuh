@@ -366,6 +366,24 @@ MT_DEVINL void timeline_end(unsigned long long* tl) {
   if (tl != nullptr && threadIdx.x == 0) atomicMax(tl + 1, globaltimer_ns());
 }
 
+// Attention dropout (Graph fork: attn_drop = 0.1): keep / drop decision of attention-matrix element (q, k) of one
+// (batch, head) as a pure function of (seed, batch*H + head, q*N + k), so that the forward kernel (one query row per
+// thread), the backward kernel (one key row per thread) and the mask-dump kernel of the tests all agree without storing
+// the mask.  lowbias32 integer hash (two multiplies): enough statistical quality for a Bernoulli mask.
+MT_DEVINL uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+MT_DEVINL uint32_t attn_drop_seed(uint32_t seed_lo, uint32_t seed_hi, uint32_t bh) {
+  return mix32(seed_lo ^ mix32(seed_hi + bh * 0x9e3779b1u));
+}
+// keep when hash >= thresh, thresh = p * 2^32
+MT_DEVINL bool attn_keep(uint32_t bh_seed, uint32_t idx, uint32_t thresh) { return mix32(idx ^ bh_seed) >= thresh; }
+
 MT_DEVINL void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

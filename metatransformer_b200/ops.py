@@ -195,8 +195,9 @@ def attention(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None,
     return out
 
 
-def attention_lse(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None):
-    """attention() that also returns lse2 [B,H,N] (fp32 log2-sum-exp of the scaled scores) for the backward."""
+def attention_lse(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None, drop_p: float = 0.0, seed: int = 0):
+    """attention() that also returns lse2 [B,H,N] (fp32 log2-sum-exp of the scaled scores) for the backward.  drop_p > 0:
+    attention dropout with the hash mask of (seed, batch, head, query, key) (attention_bwd replays it)."""
     _require_cuda(qkv)
     B, N, C3 = qkv.shape
     dh = C3 // (3 * num_heads)
@@ -205,13 +206,23 @@ def attention_lse(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = No
     out = torch.empty((B, N, num_heads * dh), dtype=torch.bfloat16, device=qkv.device)
     lse2 = torch.empty((B, num_heads, N), dtype=torch.float32, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        check(_lib.load().mt_attention_fwd_lse(qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, num_heads, dh,
-                                               float(scale), _stream()), "mt_attention_fwd_lse")
+        check(_lib.load().mt_attention_fwd_ex(qkv.data_ptr(), out.data_ptr(), lse2.data_ptr(), B, N, num_heads, dh,
+                                              float(scale), float(drop_p), int(seed) & (2 ** 64 - 1), _stream()),
+              "mt_attention_fwd_ex")
     return out, lse2
 
 
+def attention_dropout_mask(B: int, N: int, num_heads: int, drop_p: float, seed: int, device) -> torch.Tensor:
+    """The keep mask [B,H,N,N] (uint8) the attention kernels apply for (drop_p, seed): test / debugging aid."""
+    mask = torch.empty((B, num_heads, N, N), dtype=torch.uint8, device=device)
+    with torch.cuda.device(mask.device):
+        check(_lib.load().mt_attention_dropout_mask(mask.data_ptr(), B, N, num_heads, float(drop_p),
+                                                    int(seed) & (2 ** 64 - 1), _stream()), "mt_attention_dropout_mask")
+    return mask
+
+
 def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse2: torch.Tensor, num_heads: int,
-                  scale: Optional[float] = None) -> torch.Tensor:
+                  scale: Optional[float] = None, drop_p: float = 0.0, seed: int = 0) -> torch.Tensor:
     """d(qkv) [B,N,3*H*dh] bf16 of attention(); `out`/`lse2` are the forward's results, `dout` the gradient of `out`."""
     import ctypes
     _require_cuda(qkv, out, dout, lse2)
@@ -225,9 +236,9 @@ def attention_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse2
     check(lib.mt_attention_bwd_workspace_bytes(B, N, num_heads, ctypes.byref(need)), "mt_attention_bwd_workspace_bytes")
     ws = torch.empty(need.value, dtype=torch.uint8, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        check(lib.mt_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(),
-                                   ws.data_ptr(), ws.numel(), B, N, num_heads, dh, float(scale), _stream()),
-              "mt_attention_bwd")
+        check(lib.mt_attention_bwd_ex(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse2.data_ptr(), dqkv.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), B, N, num_heads, dh, float(scale), float(drop_p),
+                                      int(seed) & (2 ** 64 - 1), _stream()), "mt_attention_bwd_ex")
     return dqkv
 
 

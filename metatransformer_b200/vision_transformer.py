@@ -97,6 +97,40 @@ def _packed(module: nn.Module, name: str, param: Optional[torch.Tensor], dtype: 
     return packed
 
 
+_HD = 64   # head width of the tcgen05 attention kernels
+
+
+def _cached(module: nn.Module, name: str, sources, build):
+    """Derived tensor cached on the (storage, version, device, dtype) of its source parameters."""
+    cache = module.__dict__.setdefault("_mt_pack_cache", {})
+    key = tuple(None if q is None else (q.data_ptr(), q._version, q.device, q.dtype) for q in sources)
+    hit = cache.get(name)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = build()
+    cache[name] = (key, val)
+    return val
+
+
+def _pad_qkv_rows(t: Optional[torch.Tensor], H: int, dh: int) -> Optional[torch.Tensor]:
+    """[3*H*dh, ...] -> [3*H*64, ...] with zero rows for the padded lanes of every head (one-time weight preparation).
+    head_dim < 64 (Graph fork: 768 / 32 heads = 24) then runs on the head_dim-64 tensor-core kernels, forward and
+    backward: zero q / k lanes add nothing to q.k, zero v lanes give zero output lanes, which the zero proj columns ignore."""
+    if t is None or dh == _HD:
+        return t
+    out = t.new_zeros((3, H, _HD) + tuple(t.shape[1:]))
+    out[:, :, :dh] = t.reshape((3, H, dh) + tuple(t.shape[1:]))
+    return out.reshape((3 * H * _HD,) + tuple(t.shape[1:]))
+
+
+def _pad_proj_cols(w: torch.Tensor, H: int, dh: int) -> torch.Tensor:
+    if dh == _HD:
+        return w
+    out = w.new_zeros((w.shape[0], H, _HD))
+    out[:, :, :dh] = w.reshape(w.shape[0], H, dh)
+    return out.reshape(w.shape[0], H * _HD)
+
+
 def _check_input(x: torch.Tensor, what: str) -> None:
     if not x.is_cuda:
         raise RuntimeError(f"{what}: input is on {x.device}; metatransformer_b200 runs on B200 GPUs only and has no CPU "
@@ -169,16 +203,53 @@ class Attention(nn.Module):
 
     def _check_train(self):
         if self.training and self.attn_drop.p > 0:
-            raise NotImplementedError("Attention: attn_drop > 0 in training mode is not implemented on the B200 path "
-                                      "(the mask would have to be generated inside the attention kernels)")
+            raise NotImplementedError("Attention: attn_drop > 0 in training mode is built at Block granularity only "
+                                      "(the hash mask is generated inside the attention kernels)")
         if self.training and self.proj_drop.p > 0:
             raise NotImplementedError("Attention: proj_drop > 0 in training mode is built at Block granularity only")
 
-    def _forward_2d(self, h: torch.Tensor, B: int, N: int, residual: Optional[torch.Tensor]) -> torch.Tensor:
-        wq = _packed(self, "qkv.weight", self.qkv.weight, torch.bfloat16)
-        bq = _packed(self, "qkv.bias", self.qkv.bias, torch.float32)
-        wp = _packed(self, "proj.weight", self.proj.weight, torch.bfloat16)
+    @property
+    def head_dim(self) -> int:
+        return self.qkv.in_features // self.num_heads
+
+    def _pads(self) -> bool:
+        """head_dim < 64: the packed weights are zero-padded to 64 lanes per head (tensor-core kernels, with backward)"""
+        return self.head_dim < _HD
+
+    def _qkv_packed(self):
+        if not self._pads():
+            return (_packed(self, "qkv.weight", self.qkv.weight, torch.bfloat16),
+                    _packed(self, "qkv.bias", self.qkv.bias, torch.float32))
+        H, dh = self.num_heads, self.head_dim
+        return _cached(self, "pad.qkv", (self.qkv.weight, self.qkv.bias), lambda: (
+            ops.cast(_pad_qkv_rows(self.qkv.weight.detach().float().contiguous(), H, dh), torch.bfloat16),
+            None if self.qkv.bias is None else _pad_qkv_rows(self.qkv.bias.detach().float(), H, dh).contiguous()))
+
+    def _proj_packed(self):
         bp = _packed(self, "proj.bias", self.proj.bias, torch.float32)
+        if not self._pads():
+            return _packed(self, "proj.weight", self.proj.weight, torch.bfloat16), bp
+        H, dh = self.num_heads, self.head_dim
+        wp = _cached(self, "pad.proj", (self.proj.weight,), lambda: ops.cast(
+            _pad_proj_cols(self.proj.weight.detach().float().contiguous(), H, dh).contiguous(), torch.bfloat16))
+        return wp, bp
+
+    def _unpad_index(self, device):
+        """positions of the real (3, H, dh) rows inside the padded (3, H, 64) layout, and of the (H, dh) columns"""
+        H, dh = self.num_heads, self.head_dim
+        cache = self.__dict__.setdefault("_mt_pack_cache", {})
+        hit = cache.get("pad.idx")
+        if hit is None or hit[0].device != device:
+            lane = torch.arange(dh, device=device)
+            cols = (torch.arange(H, device=device)[:, None] * _HD + lane[None, :]).reshape(-1)
+            rows = (torch.arange(3, device=device)[:, None] * (H * _HD) + cols[None, :]).reshape(-1)
+            hit = (rows, cols)
+            cache["pad.idx"] = hit
+        return hit
+
+    def _forward_2d(self, h: torch.Tensor, B: int, N: int, residual: Optional[torch.Tensor]) -> torch.Tensor:
+        wq, bq = self._qkv_packed()
+        wp, bp = self._proj_packed()
         qkv = ops.linear(h, wq, bq)                                   # (M, 3C), packed (3, H, dh)
         o = ops.attention(qkv.view(B, N, -1), self.num_heads, self.scale)   # (B, N, C)
         return ops.linear(o.view(B * N, -1), wp, bp, residual=residual)
@@ -237,6 +308,17 @@ class Block(nn.Module):
         cache[name] = (key, folded)
         return folded
 
+    def _folded_qkv(self):
+        """(W*gamma, colsum, b + W beta) of qkv(norm1(.)), zero-padded to 64 lanes per head when head_dim < 64"""
+        attn = self.attn
+        folded = self._folded("fold.qkv", attn.qkv, self.norm1)
+        if not attn._pads():
+            return folded
+        H, dh = attn.num_heads, attn.head_dim
+        return _cached(self, "fold.qkv.pad", (attn.qkv.weight, attn.qkv.bias, self.norm1.weight, self.norm1.bias), lambda: (
+            _pad_qkv_rows(folded[0], H, dh).contiguous(), _pad_qkv_rows(folded[1], H, dh).contiguous(),
+            _pad_qkv_rows(folded[2], H, dh).contiguous()))
+
     def _forward_2d(self, x2: torch.Tensor, B: int, N: int, x2_lo: Optional[torch.Tensor] = None,
                     want_lo: bool = False):
         """(hi, lo | None) of the Block output.  The residual stream is a split pair of bf16 tensors hi + lo (16 mantissa
@@ -252,14 +334,13 @@ class Block(nn.Module):
             h = ops.layernorm(x_mid, g2, b2, self.norm2.eps, out=h)
             return self.mlp._forward_2d(h, residual=x_mid), None
         attn, mlp = self.attn, self.mlp
-        wq, csq, bq = self._folded("fold.qkv", attn.qkv, self.norm1)
+        wq, csq, bq = self._folded_qkv()
         stats = ops.row_stats(x2, self.norm1.eps, x_lo=x2_lo)
         qkv = ops.linear_ln(x2, wq, bq, csq, stats)
         o = ops.attention(qkv.view(B, N, -1), attn.num_heads, attn.scale)
         mid_lo = torch.empty_like(x2)
-        x_mid = ops.linear(o.view(B * N, -1), _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16),
-                           _packed(attn, "proj.bias", attn.proj.bias, torch.float32), residual=x2, residual_lo=x2_lo,
-                           out_lo=mid_lo)
+        wp, bp = attn._proj_packed()
+        x_mid = ops.linear(o.view(B * N, -1), wp, bp, residual=x2, residual_lo=x2_lo, out_lo=mid_lo)
         w1, cs1, b1 = self._folded("fold.fc1", mlp.fc1, self.norm2)
         stats = ops.row_stats(x_mid, self.norm2.eps, out=stats, x_lo=mid_lo)
         hid = ops.linear_ln(x_mid, w1, b1, cs1, stats, gelu=True)
@@ -285,7 +366,8 @@ class Block(nn.Module):
 
     def _is_stochastic(self) -> bool:
         p_path = self.drop_path.drop_prob if isinstance(self.drop_path, DropPath) else 0.0
-        return self.training and (self.attn.proj_drop.p > 0 or self.mlp.drop.p > 0 or p_path > 0)
+        return self.training and (self.attn.proj_drop.p > 0 or self.mlp.drop.p > 0 or p_path > 0
+                                  or self.attn.attn_drop.p > 0)
 
     @staticmethod
     def _replay(g: torch.Tensor, p: float, key, rs, N: int) -> torch.Tensor:
@@ -299,11 +381,13 @@ class Block(nn.Module):
         (attention.py:37, mlp.py:31-34) and per-sample DropPath on both residual branches (attention.py:56-57)."""
         if not self.training:
             return None
-        p_proj, p_mlp = self.attn.proj_drop.p, self.mlp.drop.p
+        p_proj, p_mlp, p_attn = self.attn.proj_drop.p, self.mlp.drop.p, self.attn.attn_drop.p
         p_path = self.drop_path.drop_prob if isinstance(self.drop_path, DropPath) else 0.0
-        if p_proj == 0 and p_mlp == 0 and p_path == 0:
+        if p_proj == 0 and p_mlp == 0 and p_path == 0 and p_attn == 0:
             return None
-        cfg = {"p_proj": p_proj, "p_mlp": p_mlp, "rs1": None, "rs2": None}
+        # "plain": only the attention dropout is active — the residual GEMMs keep their fused residual adds
+        cfg = {"p_proj": p_proj, "p_mlp": p_mlp, "p_attn": p_attn, "seed_attn": 0, "rs1": None, "rs2": None,
+               "plain": p_proj == 0 and p_mlp == 0 and p_path == 0}
         if p_path > 0:
             keep = 1.0 - p_path
             rs = torch.empty((2, B), dtype=torch.float32, device=device).bernoulli_(keep).div_(keep)   # timm DropPath
@@ -314,13 +398,20 @@ class Block(nn.Module):
         """Forward that keeps what the backward needs (qkv, attention output + lse, the pre-GELU activation)."""
         attn, mlp = self.attn, self.mlp
         drop = self._drop_config(B, x2.device)
-        wq, csq, bq = self._folded("fold.qkv", attn.qkv, self.norm1)
+        wq, csq, bq = self._folded_qkv()
         stats1 = ops.row_stats(x2, self.norm1.eps)
         qkv = ops.linear_ln(x2, wq, bq, csq, stats1)
-        o, lse2 = ops.attention_lse(qkv.view(B, N, -1), attn.num_heads, attn.scale)
-        wp = _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16)
-        bp = _packed(attn, "proj.bias", attn.proj.bias, torch.float32)
-        if drop is None:
+        if drop is not None and drop["p_attn"] > 0:
+            # attention dropout (attention.py:33): hash mask keyed on a 64-bit draw from torch's CUDA generator, replayed
+            # by the backward kernel
+            sd_, off_ = _philox_reserve(x2.device, B * attn.num_heads * N * N)
+            drop["seed_attn"] = (sd_ ^ (off_ * 0x9E3779B97F4A7C15)) & (2 ** 64 - 1)
+        o, lse2 = ops.attention_lse(qkv.view(B, N, -1), attn.num_heads, attn.scale,
+                                    drop_p=0.0 if drop is None else drop["p_attn"],
+                                    seed=0 if drop is None else drop["seed_attn"])
+        wp, bp = attn._proj_packed()
+        plain = drop is None or drop["plain"]
+        if plain:
             x_mid = ops.linear(o.view(B * N, -1), wp, bp, residual=x2)
         else:
             branch = ops.linear(o.view(B * N, -1), wp, bp)
@@ -333,7 +424,7 @@ class Block(nn.Module):
         hid = ops.gelu(u)
         w2 = _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16)
         b2 = _packed(mlp, "fc2.bias", mlp.fc2.bias, torch.float32)
-        if drop is None:
+        if plain:
             out = ops.linear(hid, w2, b2, residual=x_mid)
         else:
             if drop["p_mlp"] > 0:
@@ -351,7 +442,8 @@ class Block(nn.Module):
         attn, mlp = self.attn, self.mlp
         M = B * N
         # gradient entering the mlp branch (after its dropout / stochastic depth, replayed from the saved Philox keys)
-        gb2 = g2 if drop is None else self._replay(g2, drop["p_mlp"], drop["k2"], drop["rs2"], N)
+        plain = drop is None or drop["plain"]
+        gb2 = g2 if plain else self._replay(g2, drop["p_mlp"], drop["k2"], drop["rs2"], N)
         w2t = self._transposed("t.fc2", _packed(mlp, "fc2.weight", mlp.fc2.weight, torch.bfloat16), mlp.fc2.weight)
         du = ops.linear_gelu_grad(gb2, w2t, u)                                  # dL/du = (g W2) * gelu'(u)
         if drop is not None and drop["p_mlp"] > 0:
@@ -359,11 +451,13 @@ class Block(nn.Module):
         w1f = self._folded("fold.fc1", mlp.fc1, self.norm2)[0]
         dxh2 = ops.linear(du, self._transposed("t.fc1f", w1f, mlp.fc1.weight, self.norm2.weight))                  # dL/dxhat (gamma already folded in)
         g1 = ops.layernorm_bwd(dxh2, x_mid, stats2, None, add=g2)               # + residual branch
-        gb1 = g1 if drop is None else self._replay(g1, drop["p_proj"], drop["k1"], drop["rs1"], N)
-        wpt = self._transposed("t.proj", _packed(attn, "proj.weight", attn.proj.weight, torch.bfloat16), attn.proj.weight)
+        gb1 = g1 if plain else self._replay(g1, drop["p_proj"], drop["k1"], drop["rs1"], N)
+        wpt = self._transposed("t.proj", attn._proj_packed()[0], attn.proj.weight)
         do = ops.linear(gb1, wpt)
-        dqkv = ops.attention_bwd(qkv.view(B, N, -1), o, do.view(B, N, -1), lse2, attn.num_heads, attn.scale)
-        wqf = self._folded("fold.qkv", attn.qkv, self.norm1)[0]
+        dqkv = ops.attention_bwd(qkv.view(B, N, -1), o, do.view(B, N, -1), lse2, attn.num_heads, attn.scale,
+                                 drop_p=0.0 if drop is None else drop["p_attn"],
+                                 seed=0 if drop is None else drop["seed_attn"])
+        wqf = self._folded_qkv()[0]
         dxh1 = ops.linear(dqkv.view(M, -1), self._transposed("t.qkvf", wqf, attn.qkv.weight, self.norm1.weight))
         dx = ops.layernorm_bwd(dxh1, x2, stats1, None, add=g1)
         return dx, (gb2, du, gb1, dqkv.view(M, -1))
@@ -405,10 +499,16 @@ class Block(nn.Module):
         # --- attn.proj: input o ---
         dwp = ops.linear_wgrad(g1, o.view(o.shape[0] * o.shape[1], -1))
         dbp = ops.colsum(g1)
+        if attn._pads():                       # drop the zero-padded head lanes again (weight-gradient re-layout)
+            rows_idx, cols_idx = attn._unpad_index(x2.device)
+            dwp = dwp.index_select(1, cols_idx).contiguous()
         # --- attn.qkv (norm1 folded): input xhat1 ---
         xh = ops.layernorm(x2, ones, zeros, self.norm1.eps, out=xh)
         dwf = ops.linear_wgrad(dqkv, xh)
         dybq = ops.colsum(dqkv)
+        if attn._pads():
+            dwf = dwf.index_select(0, rows_idx).contiguous()
+            dybq = dybq.index_select(0, rows_idx).contiguous()
         dwq, dg1, dbt1 = ops.ln_fold_bwd(dwf, attn.qkv.weight.detach().contiguous(), f32(self.norm1.weight),
                                          f32(self.norm1.bias), dybq)
         return [dg1, dbt1, dwq, dybq if attn.qkv.bias is not None else None, dwp, dbp, dg2, dbt2, dw1, dyb1, dw2, db2]
@@ -420,9 +520,6 @@ class Block(nn.Module):
         if pos is not None:
             x = _AddPosFn.apply(x, pos)
         _check_input(x, "Block")
-        if self.training and self.attn.attn_drop.p > 0:
-            raise NotImplementedError("Block: attn_drop > 0 in training mode is not implemented on the B200 path (the "
-                                      "mask would have to be generated inside the attention kernels); drop / drop_path are")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return _BlockFn.apply(x, self, *[p for p in self._param_list() if p is not None])
         B, N, C = x.shape

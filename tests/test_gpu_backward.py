@@ -169,3 +169,36 @@ def test_splitk_weight_gradient_gemm(mt, M, N, K, splits, via_transpose):
     dw = mt.ops.linear_wgrad(dy.cuda().bfloat16(), x.cuda().bfloat16(), splits, via_transpose=via_transpose)
     assert dw.dtype == torch.float32 and dw.shape == (N, K)
     _assert_close(dw, ref, rel=1e-4, mx=1e-4, what=f"split-K wgrad {M}x{N}x{K} via_transpose={via_transpose}")
+
+
+@pytest.mark.parametrize("dim,heads", [(768, 32), (96, 3)])
+def test_graph_fork_head_dim_below_64_trains_on_tensor_cores(mt, dim, heads):
+    """Graph fork geometry (Graph/metatransformer/modules/tokengt_graph_encoder.py:193-203: dim 768, 32 heads -> head_dim
+    24): the packed weights are zero-padded to 64 lanes per head, forward and backward run on the tcgen05 attention
+    kernels; output, input gradient and all 12 parameter gradients vs fp64 autograd of the oracle."""
+    sd = orc.make_encoder_state_dict(dim, 1, seed=12)
+    sd = {k: (_bf16_round(v) if v.dim() == 2 else v) for k, v in sd.items()}
+    blk = mt.Block(dim=dim, num_heads=heads, mlp_ratio=4., qkv_bias=True, norm_layer=torch.nn.LayerNorm,
+                   act_layer=torch.nn.GELU)
+    blk.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+    blk = blk.cuda().train()
+    g = torch.Generator().manual_seed(5)
+    B, N = 3, 70
+    x = _bf16_round(torch.randn(B, N, dim, generator=g))
+    gy = _bf16_round(torch.randn(B, N, dim, generator=g) * 0.05)
+    ref_p = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    xr = x.double().requires_grad_(True)
+    yr = orc.encoder(xr, ref_p, 1, heads)
+    yr.backward(gy.double())
+    xg = x.cuda().bfloat16().requires_grad_(True)
+    y = blk(xg)
+    _assert_close(y, yr.detach(), what=f"Block dim={dim} heads={heads} forward")
+    y.backward(gy.cuda().bfloat16())
+    _assert_close(xg.grad, xr.grad, rel=2e-2, mx=2e-2, what="dL/dx")
+    for name, prm in blk.named_parameters():
+        ref = ref_p["0." + name].grad
+        assert prm.grad is not None and prm.grad.shape == ref.shape, name
+        rel = float((prm.grad.double().cpu() - ref).norm() / ref.norm().clamp_min(1e-12))
+        assert rel <= 3e-2, f"{name}: rel_l2 {rel:.3e}"
+    with torch.no_grad():
+        _assert_close(blk.eval()(x.cuda()), yr.detach(), what="eval forward, fp32 tokens")

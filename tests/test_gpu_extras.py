@@ -283,10 +283,56 @@ def test_dropout_follows_torch_cuda_rng_and_checkpointing(mt):
         blk.eval()
         ye1, ye2 = blk(x), blk(x)
         assert torch.equal(ye1, ye2) and not torch.equal(ye1, y1)
-    blk.train()
-    blk.attn.attn_drop.p = 0.1
-    with pytest.raises(NotImplementedError):
-        blk(x)
+
+
+@pytest.mark.parametrize("B,N,H,p", [(2, 196, 3, 0.1), (1, 300, 2, 0.25), (2, 64, 1, 0.5)])
+def test_attention_dropout_forward_backward_match_oracle_with_the_same_mask(mt, B, N, H, p):
+    """attn = softmax(q k^T scale); attn = keep * attn / (1 - p); out = attn @ v (attention.py:31-35 with attn_drop > 0).
+    The kernels generate keep(b, h, q, k) from a hash; mt_attention_dropout_mask dumps the same mask for the fp64 oracle."""
+    g = torch.Generator().manual_seed(N + H)
+    C = H * 64
+    seed = 0x1234_5678_9ABC_DEF0 + N
+    qkv = _bf16_round(torch.randn(B, N, 3 * C, generator=g))
+    do = _bf16_round(torch.randn(B, N, C, generator=g))
+    keep = mt.ops.attention_dropout_mask(B, N, H, p, seed, "cuda").cpu().double()
+    frac = keep.mean().item()
+    assert abs(frac - (1 - p)) < 0.01, f"keep fraction {frac:.4f} vs {1 - p}"
+    assert abs(keep[:, :, :, ::2].mean().item() - (1 - p)) < 0.015 and abs(keep[:, :, ::2].mean().item() - (1 - p)) < 0.015
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = qr.reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)
+    a = ((q @ k.transpose(-2, -1)) * 0.125).softmax(-1) * keep / (1 - p)
+    ref = (a @ v).transpose(1, 2).reshape(B, N, C)
+    ref.backward(do.double())
+    qd = qkv.cuda().bfloat16()
+    out, lse2 = mt.ops.attention_lse(qd, H, drop_p=p, seed=seed)
+    _assert_close(out, ref.detach(), what=f"attention + dropout({p}) forward")
+    dqkv = mt.ops.attention_bwd(qd, out, do.cuda().bfloat16(), lse2, H, drop_p=p, seed=seed)
+    _assert_close(dqkv, qr.grad, rel=2e-2, mx=2e-2, what=f"attention + dropout({p}) backward")
+    out2, _ = mt.ops.attention_lse(qd, H, drop_p=p, seed=seed + 1)
+    assert not torch.equal(out2, out)
+
+
+def test_graph_fork_block_trains_with_attn_drop(mt):
+    """Graph fork Block (dim 768, 32 heads, attn_drop 0.1; tokengt_graph_encoder.py:193-203) in training mode: runs through
+    the tcgen05 kernels, masks follow torch's CUDA generator, eval mode is deterministic and mask-free."""
+    torch.manual_seed(0)
+    blk = mt.Block(dim=768, num_heads=32, mlp_ratio=4., qkv_bias=True, drop=0.0, attn_drop=0.1).cuda().train()
+    x = torch.randn(4, 50, 768, device="cuda").requires_grad_(True)
+    torch.cuda.manual_seed(11)
+    y1 = blk(x)
+    y1.float().square().mean().backward()
+    assert torch.isfinite(x.grad).all() and all(torch.isfinite(q.grad).all() for q in blk.parameters())
+    torch.cuda.manual_seed(11)
+    y2 = blk(x)
+    torch.cuda.manual_seed(12)
+    y3 = blk(x)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    blk.eval()
+    with torch.no_grad():
+        e1, e2 = blk(x), blk(x)
+    assert torch.equal(e1, e2)
+    rel = float((y1.detach() - e1).norm() / e1.norm())
+    assert 1e-4 < rel < 0.2, f"train-vs-eval relative difference {rel:.3e}"
 
 
 # ---------------------------------------------------------------------------------------------------------------
