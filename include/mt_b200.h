@@ -53,6 +53,10 @@ int mt_gemm_bf16(const void* x, const void* w, const float* bias, const void* re
  * (attention.py:56 `attn(norm1(x))` -> qkv, :57 `mlp(norm2(x))` -> fc1).                                      */
 int mt_row_stats(const void* x, int x_dtype, float* stats /* [M][2] = mean, rstd */, int M, int d, float eps,
                  void* stream);
+/* (mean, rstd) per row from the statistics records a residual GEMM emitted with `out_row_sums` (see mt_gemm_opts):
+ * records [M][ceil(d/64)][4] -> stats [M][2].  One tiny pass instead of every CTA column of the consuming GEMM
+ * re-reading (and re-combining) all the records of its rows.                                                      */
+int mt_ln_stats_finalize(const float* records, float* stats, int M, int d, float eps, void* stream);
 /* same for a split (hi + lo) bf16 row: statistics of hi + lo in fp32 */
 int mt_row_stats_split(const void* x_hi, const void* x_lo, float* stats, int M, int d, float eps, void* stream);
 /* Entry transform of the whole-encoder driver: c_row[m] = mean(x[m,:]); (hi, lo) = split(x - c_row) as bf16 [M,d] each;

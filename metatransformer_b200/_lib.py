@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "mt_im2row", "mt_im2row1d_circular", "mt_prepend_row", "mt_assemble_tokens", "mt_pool_layernorm", "mt_pool_layernorm_bwd",
     "mt_dropout", "mt_pad_cols", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
     "mt_encoder_forward", "mt_encoder_forward_ex", "mt_encoder_launches_per_forward",
-    "mt_row_stats_split", "mt_center_split", "mt_embed_sum", "mt_split_f32", "mt_merge_f32", "mt_timeline_begin", "mt_timeline_end", "mt_allreduce", "mt_attention_fwd_ex", "mt_attention_bwd_ex",
+    "mt_row_stats_split", "mt_ln_stats_finalize", "mt_center_split", "mt_embed_sum", "mt_split_f32", "mt_merge_f32", "mt_timeline_begin", "mt_timeline_end", "mt_allreduce", "mt_attention_fwd_ex", "mt_attention_bwd_ex",
     "mt_attention_dropout_mask",
 )
 
@@ -132,6 +132,8 @@ def _declare(lib: ctypes.CDLL) -> None:
                                           c_void_p]
     lib.mt_row_stats_split.restype = c_int
     lib.mt_row_stats_split.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]
+    lib.mt_ln_stats_finalize.restype = c_int
+    lib.mt_ln_stats_finalize.argtypes = [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]
     lib.mt_center_split.restype = c_int
     lib.mt_center_split.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]
     lib.mt_embed_sum.restype = c_int

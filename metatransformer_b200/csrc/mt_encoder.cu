@@ -21,7 +21,7 @@ struct mt_encoder {
 
 namespace {
 struct WsLayout {
-  size_t h, qkv, attn, mid, mid_lo, xo0, xo1, xo0_lo, xo1_lo, hid, stats, stats2, crow, total;
+  size_t h, qkv, attn, mid, mid_lo, xo0, xo1, xo0_lo, xo1_lo, hid, stats, stats2, crow, mr, total;
 };
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 WsLayout ws_layout(const mt_encoder* e, size_t M) {
@@ -42,6 +42,7 @@ WsLayout ws_layout(const mt_encoder* e, size_t M) {
   w.stats = take(M * 8 * slots);   // float4 per (row, 64-column slice)
   w.stats2 = take(M * 8 * slots);
   w.crow = take(M * 2);            // one float per row
+  w.mr = take(M * 4);              // (mean, rstd) per row
   w.total = off;
   return w;
 }
@@ -85,11 +86,11 @@ extern "C" int mt_encoder_workspace_bytes(const mt_encoder* enc, int B, int N, s
   return MT_OK;
 }
 
-// kernels per forward (bf16 in / bf16 out): 5 per Block (4 GEMMs + attention) + 1 statistics pass with folded
-// LayerNorms (the default); 7 per Block otherwise.  fp32 input / output add one split / merge pass each.
+// kernels per forward: 7 per Block either way — folded LayerNorms (default): 4 GEMMs + attention + 2 statistics
+// finalisations (the first one is the entry pass for layer 0); un-folded: 4 GEMMs + attention + 2 LayerNorm kernels.
 extern "C" int mt_encoder_launches_per_forward(const mt_encoder* enc) {
   if (!enc) return 0;
-  return enc->blocks[0].qkv_colsum ? 5 * enc->depth + 1 : 7 * enc->depth;
+  return enc->blocks[0].qkv_colsum ? 7 * enc->depth : 7 * enc->depth;
 }
 
 extern "C" int mt_encoder_forward_ex(mt_encoder* enc, const void* x, int x_dtype, void* y, int y_dtype, int B, int N,
@@ -128,10 +129,11 @@ extern "C" int mt_encoder_forward_ex(mt_encoder* enc, const void* x, int x_dtype
   // entry pass centres and splits the input into the buffers layer 0 does not write (xo[1]) and leaves the statistics of
   // layer 0's first LayerNorm; the last residual GEMM adds c_row back.
   float* c_row = reinterpret_cast<float*>(ws + w.crow);
+  float* mean_rstd = reinterpret_cast<float*>(ws + w.mr);
   const void* cur = x;
   const void* cur_lo = nullptr;
   if (folded) {
-    if ((rc = mt_center_split(x, x_dtype, xo[1], xo_lo[1], c_row, stats_a, M, d, enc->eps, stream))) return rc;
+    if ((rc = mt_center_split(x, x_dtype, xo[1], xo_lo[1], c_row, mean_rstd, M, d, enc->eps, stream))) return rc;
     cur = xo[1];
     cur_lo = xo_lo[1];
   } else if (x_dtype == MT_DT_F32) {
@@ -146,19 +148,18 @@ extern "C" int mt_encoder_forward_ex(mt_encoder* enc, const void* x, int x_dtype
     if (folded) {
       // Folded LayerNorms.  Layer 0's statistics come from the entry pass; every other LayerNorm input is produced by a
       // residual GEMM (proj / fc2) whose epilogue emits per-row shifted partial sums.
-      const int slots = (d + 63) / 64;   // statistics records per row written by a GEMM with N = d
       mt_gemm_opts o = {};
-      o.bias = bw.qkv_b; o.ln_colsum = bw.qkv_colsum; o.ln_row_stats = stats_a; o.ln_stats_are_sums = (l > 0) ? slots : 0;
-      o.ln_eps = enc->eps;
+      // the statistics records of the previous layer's fc2 epilogue -> (mean, rstd) per row (layer 0: from the entry pass)
+      if (l > 0 && (rc = mt_ln_stats_finalize(stats_a, mean_rstd, M, d, enc->eps, stream))) return rc;
+      o.bias = bw.qkv_b; o.ln_colsum = bw.qkv_colsum; o.ln_row_stats = mean_rstd;
       if ((rc = mt_gemm_bf16_ex(cur, bw.qkv_w, qkv, M, 3 * d, d, &o, stream))) return rc;
       if ((rc = mt_attention_fwd(qkv, attn, B, N, enc->heads, 64, scale, stream))) return rc;
       o = mt_gemm_opts{};
       o.bias = bw.proj_b; o.residual = cur; o.residual_lo = cur_lo; o.y_lo = mid_lo; o.out_row_sums = stats_b;
       if ((rc = mt_gemm_bf16_ex(attn, bw.proj_w, mid, M, d, d, &o, stream))) return rc;
       o = mt_gemm_opts{};
-      o.bias = bw.fc1_b; o.act = 1; o.ln_colsum = bw.fc1_colsum; o.ln_row_stats = stats_b;
-      o.ln_stats_are_sums = slots;
-      o.ln_eps = enc->eps;
+      if ((rc = mt_ln_stats_finalize(stats_b, mean_rstd, M, d, enc->eps, stream))) return rc;
+      o.bias = bw.fc1_b; o.act = 1; o.ln_colsum = bw.fc1_colsum; o.ln_row_stats = mean_rstd;
       if ((rc = mt_gemm_bf16_ex(mid, bw.fc1_w, hid, M, enc->hidden, d, &o, stream))) return rc;
       o = mt_gemm_opts{};
       o.bias = bw.fc2_b; o.residual = mid; o.residual_lo = mid_lo; o.y_lo = outp_lo;

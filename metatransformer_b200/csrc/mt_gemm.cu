@@ -344,52 +344,76 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int as = 0;
     uint32_t aphase = 0;
     bool store_pending = false;
+    auto load_bias = [&](int t_) {
+      float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t_ < num_tiles) {
+        const int n_tile_ = (t_ / p.split_k) % p.num_n_tiles;
+        const float* src = (lane < 16) ? p.bias : p.colsum;
+        const int c = n_tile_ * kBN + kEpiCols * cq + 4 * (lane & 15);
+        if (src != nullptr && c < p.N) v4 = __ldg(reinterpret_cast<const float4*>(src + c));
+      }
+      return v4;
+    };
+    auto load_stat = [&](int t_) {
+      float2 st = make_float2(0.f, 1.f);
+      if (do_ln && p.ln_sums == 0 && t_ < num_tiles) {
+        const int m_tile_ = (t_ / p.split_k) / p.num_n_tiles;
+        const int row_ = m_tile_ * (kBM * CG) + int(rank) * kBM + 32 * q + lane;
+        if (row_ < p.M) st = __ldg(reinterpret_cast<const float2*>(p.row_stats) + row_);
+      }
+      return st;
+    };
+    float4 bias_pf = load_bias(cluster_id);
+    float2 stat_pf = load_stat(cluster_id);
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int tile = t / p.split_k;
       const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
       const int row0 = m_tile * (kBM * CG) + int(rank) * kBM + 32 * q;  // first row of this warp
       const int col0 = n_tile * kBN + kEpiCols * cq;                    // first column of this warp
       const int row = row0 + lane;
-      // bias (lanes 0-15) and LN-fold column sums (lanes 16-31) of this warp's 64 columns -> private smem
-      {
-        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* src = (lane < 16) ? p.bias : p.colsum;
-        const int c = col0 + 4 * (lane & 15);
-        if (src != nullptr && c < p.N) v4 = *reinterpret_cast<const float4*>(src + c);
-        __syncwarp();
-        const_cast<float4*>(bias_s4)[lane] = v4;
-        __syncwarp();
-      }
+      // bias (lanes 0-15) and LN-fold column sums (lanes 16-31) of this warp's 64 columns -> private smem; the values
+      // were requested one tile ahead (their L2 latency used to stall every tile's first instruction)
+      __syncwarp();
+      const_cast<float4*>(bias_s4)[lane] = bias_pf;
+      __syncwarp();
       float ln_rstd = 1.f, ln_nmr = 0.f;  // rstd and -mean*rstd of this thread's row
       if (do_ln && row < p.M) {
         float mean, rstd;
         if (p.ln_sums > 0) {
           // Combine the per-slice shifted sums in one streaming pass: every slice is re-referenced to the first slice's
           // shift (d = shift_i - ref: S1 += s1_i + n_i d, S2 += s2_i + 2 d s1_i + n_i d^2), so the loads are independent
-          // of each other (unrolled: all in flight at once) and nothing cancels: ref is within a few sigma of the mean.
+          // of each other (all in flight at once) and nothing cancels: ref is within a few sigma of the mean.
+          // (mt_ln_stats_finalize does the same once per row; the whole-encoder driver uses that, because every CTA
+          // column of a wide GEMM would otherwise re-read all the records of its rows.)
           const float4* ps = reinterpret_cast<const float4*>(p.row_stats) + size_t(row) * p.ln_sums;
-          const float ref = __ldg(&ps[0].x);
+          float4 rec[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rec[i] = (i < p.ln_sums) ? __ldg(ps + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float ref = rec[0].x;
           float S1 = 0.f, S2 = 0.f;
-#pragma unroll 4
-          for (int i = 0; i < p.ln_sums; ++i) {
-            const float4 r = __ldg(ps + i);
-            const float n_i = float(min(64, p.K - 64 * i));
-            const float dd = r.x - ref;
-            S1 += fmaf(n_i, dd, r.y);
-            S2 += fmaf(dd, fmaf(n_i, dd, 2.0f * r.y), r.z);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < p.ln_sums) {
+              const float n_i = float(min(64, p.K - 64 * i));
+              const float dd = rec[i].x - ref;
+              S1 += fmaf(n_i, dd, rec[i].y);
+              S2 += fmaf(dd, fmaf(n_i, dd, 2.0f * rec[i].y), rec[i].z);
+            }
           }
           const float inv_k = 1.0f / float(p.K);
           const float m1 = S1 * inv_k;
           mean = ref + m1;
           rstd = rsqrtf(fmaxf(fmaf(S2, inv_k, -m1 * m1), 0.f) + p.ln_eps);
         } else {
-          const float2 st = reinterpret_cast<const float2*>(p.row_stats)[row];
-          mean = st.x;
-          rstd = st.y;
+          mean = stat_pf.x;
+          rstd = stat_pf.y;
         }
         ln_rstd = rstd;
         ln_nmr = -mean * rstd;
       }
+      // request the next tile's bias / column sums / row statistics now
+      bias_pf = load_bias(t + num_clusters);
+      stat_pf = load_stat(t + num_clusters);
       const uint64_t ln_rstd2 = pack_f32x2(ln_rstd, ln_rstd), ln_nmr2 = pack_f32x2(ln_nmr, ln_nmr);
       uint64_t roff2 = pack_f32x2(0.f, 0.f);
       if constexpr (kHiLo) {

@@ -213,6 +213,34 @@ center_split_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
   timeline_end(tl);
 }
 
+// LayerNorm statistics records of a residual GEMM ([M][S][4]: shift, sum(v - shift), sum((v - shift)^2), -; one per
+// 64-column slice, see mt_gemm.cu) -> (mean, rstd) per row.  One thread per row, the S <= 64 records of a row are
+// contiguous (S * 16 bytes); every slice is re-referenced to the first slice's shift, so nothing cancels.
+__global__ void __launch_bounds__(256)
+ln_stats_finalize_kernel(const float4* __restrict__ rec, float2* __restrict__ stats, int M, int S, int d, float eps,
+                         unsigned long long* tl) {
+  timeline_start(tl);
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < M) {
+    const float4* ps = rec + size_t(row) * S;
+    const float ref = ps[0].x;
+    float S1 = 0.f, S2 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < S; ++i) {
+      const float4 r = ps[i];
+      const float n_i = float(min(64, d - 64 * i));
+      const float dd = r.x - ref;
+      S1 += fmaf(n_i, dd, r.y);
+      S2 += fmaf(dd, fmaf(n_i, dd, 2.0f * r.y), r.z);
+    }
+    const float inv_d = 1.0f / float(d);
+    const float m1 = S1 * inv_d;
+    stats[row] = make_float2(ref + m1, rsqrtf(fmaxf(fmaf(S2, inv_d, -m1 * m1), 0.f) + eps));
+  }
+  __syncthreads();
+  timeline_end(tl);
+}
+
 // same for a split (hi + lo) row: the statistics of hi + lo (residual stream of the per-Block path)
 __global__ void __launch_bounds__(kLnWarps * 32)
 row_stats_split_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, float2* __restrict__ stats,
@@ -354,6 +382,19 @@ extern "C" int mt_center_split(const void* x, int x_dtype, void* hi, void* lo, f
     set_error("mt_center_split: x_dtype must be bf16 or fp32 (got %d)", x_dtype);
     return MT_ERR_BAD_DTYPE;
   }
+  MT_CHECK_CUDA(cudaGetLastError());
+  return MT_OK;
+}
+
+extern "C" int mt_ln_stats_finalize(const float* records, float* stats, int M, int d, float eps, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(records && stats, MT_ERR_BAD_SHAPE, "mt_ln_stats_finalize: null pointer");
+  MT_REQUIRE(M > 0 && d > 0, MT_ERR_BAD_SHAPE, "mt_ln_stats_finalize: M and d must be positive");
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(records) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+             MT_ERR_BAD_ALIGN, "mt_ln_stats_finalize: records 16-byte, stats 8-byte aligned");
+  ln_stats_finalize_kernel<<<unsigned(ceil_div(M, 256)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(records), reinterpret_cast<float2*>(stats), M, (d + 63) / 64, d, eps,
+      timeline_next_slot());
   MT_CHECK_CUDA(cudaGetLastError());
   return MT_OK;
 }

@@ -18,7 +18,9 @@ from . import _lib
 def kernel_names(depth: int) -> List[str]:
     names = ["center_split"]
     for l in range(depth):
-        names += [f"L{l}.qkv", f"L{l}.attention", f"L{l}.proj", f"L{l}.fc1", f"L{l}.fc2"]
+        if l > 0:
+            names.append(f"L{l}.stats1")
+        names += [f"L{l}.qkv", f"L{l}.attention", f"L{l}.proj", f"L{l}.stats2", f"L{l}.fc1", f"L{l}.fc2"]
     return names
 
 
