@@ -460,6 +460,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int pc = 0; pc < kEpiCols / kPiece; ++pc) load_hi(pc, rh[pc]);
           load_lo(0, rl[0]);
+          // When the epilogue is the slower side it never idles, so the loads above are issued exactly when their data
+          // is needed and the whole HBM latency would be exposed once per tile: pull the NEXT tile's 128-byte row
+          // segments (hi and lo) into L2 now, one tile ahead.
+          const int t_n = t + num_clusters;
+          if (t_n < num_tiles) {
+            const int tile_n = t_n / p.split_k;
+            const int row_n = (tile_n / p.num_n_tiles) * (kBM * CG) + int(rank) * kBM + 32 * q + lane;
+            const int col_n = (tile_n % p.num_n_tiles) * kBN + kEpiCols * cq;
+            if (row_n < p.M && col_n < p.N) {
+              const size_t off = size_t(row_n) * p.ldr + col_n;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + off));
+              if (p.resid_lo != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid_lo + off));
+            }
+          }
         } else {
           load_hi(0, rh[0]);
         }
