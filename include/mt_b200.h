@@ -229,6 +229,23 @@ int mt_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, 
 int mt_split_f32(const float* src, void* hi, void* lo, size_t n, void* stream);
 int mt_merge_f32(const void* hi, const void* lo, float* dst, size_t n, void* stream);
 
+/* ---- E7: fp32-accuracy path (plain-fp32 callers: X-Ray/train.py:52-60; north_star gate 1e-4) ----------------------
+ * Linear layers as "3xTF32" on the tensor cores: every fp32 operand is a PAIR big = x with the low 13 mantissa bits
+ * cleared (exact in TF32) and small = x - big; x.w = small_x.big_w + big_x.small_w + big_x.big_w with fp32
+ * accumulation (tcgen05.mma.kind::tf32).  Producers write pairs directly; the residual stream is plain fp32.
+ *   mt_split_tf32:          src -> (big, small), n % 4 == 0 (weights, once)
+ *   mt_layernorm_f32_split: LayerNorm (fp32, two-pass statistics) -> (big, small)
+ *   mt_gemm_f32x3:          y = act(x.w^T + bias) (+ residual fp32); y_small == NULL: y is the fp32 result, else (y,
+ *                           y_small) is its pair (feeds the next GEMM); act 0 | 1 (exact-erf GELU); K % 4, N % 16 == 0
+ *   mt_attention_f32:       softmax(q k^T scale) v on fp32 qkv [B,N,3,H,dh] (dh 16 | 24 | 32 | 64), SIMT, output pair  */
+int mt_split_tf32(const float* src, float* big, float* small, size_t n, void* stream);
+int mt_layernorm_f32_split(const float* x, const float* gamma, const float* beta, float* big, float* small, int M, int d,
+                           float eps, void* stream);
+int mt_gemm_f32x3(const float* x_big, const float* x_small, const float* w_big, const float* w_small, const float* bias,
+                  const float* residual, float* y, float* y_small, int M, int N, int K, int act, void* stream);
+int mt_attention_f32(const float* qkv, float* out_big, float* out_small, int B, int N, int H, int dh, float scale,
+                     void* stream);
+
 /* ---- E8: gradient all-reduce for integrators that own an NCCL communicator ------------------------------------------
  * In place: buf = scale * sum over ranks of buf (scale = 1 / world_size for DDP averaging,
  * Video/run_class_finetuning.py:739-741).  `nccl_comm` is the caller's ncclComm_t; ncclAllReduce is resolved with dlopen

@@ -18,7 +18,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libmt_b200.so"
-SOURCES = ["mt_capi.cu", "mt_gemm.cu", "mt_layernorm.cu", "mt_attention.cu", "mt_patch_embed.cu", "mt_encoder.cu", "mt_backward.cu", "mt_attention_bwd.cu", "mt_attention_generic.cu", "mt_head.cu"]
+SOURCES = ["mt_capi.cu", "mt_gemm.cu", "mt_layernorm.cu", "mt_attention.cu", "mt_patch_embed.cu", "mt_encoder.cu", "mt_backward.cu", "mt_attention_bwd.cu", "mt_attention_generic.cu", "mt_head.cu", "mt_fp32.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

@@ -24,6 +24,9 @@
 // 9 = S=QK^T issuer + TMEM allocator, 10 = O+=PV issuer, 11 idle (completes the third warpgroup for setmaxnreg).
 // a timed-out barrier wait traps without the device printf: the call sequence costs the 40-register role warps spills
 #define MT_WAIT_QUIET 1
+#ifndef MT_ATTN_ONE_PASS
+#define MT_ATTN_ONE_PASS 0   // 1: whole score row in registers (does not fit 96 registers: kept for A/B builds only)
+#endif
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 
@@ -292,26 +295,54 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         mbar_wait(s_full(t), n_sf & 1u);
         ++n_sf;
         tc_fence_after();
-        // ---- pass 1: row maximum straight from TMEM, one 16-key quarter at a time (a whole 64-column score row plus
-        //      the exp / pack temporaries does not fit the 96 registers a two-CTA-per-SM softmax thread has; TMEM reads
-        //      are cheap, so pass 2 simply loads the quarters again).  Padded keys of the last quarter -> -inf. ----
+#if MT_ATTN_ONE_PASS
+        // whole 64-column score row in registers: S_t is released to the tensor core right after the loads
+        uint32_t s[64];
+        tmem_ld_32x32b_x16_at<0>(ts, s);
+        if (nq > 1) tmem_ld_32x32b_x16_at<16>(ts + 16u, s);
+        if (nq > 2) tmem_ld_32x32b_x16_at<32>(ts + 32u, s);
+        if (nq > 3) tmem_ld_32x32b_x16_at<48>(ts + 48u, s);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(t));
         float m_tile = -INFINITY;
 #pragma unroll
         for (int qi = 0; qi < 4; ++qi) {
           if (qi < nq) {
-            uint32_t sq[16];
-            tmem_ld_32x32b_x16(ts + uint32_t(16 * qi), sq);
-            tmem_wait_ld();
             if (tail != 0 && qi == nq - 1) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) m_tile = fmaxf(m_tile, (i < tail) ? __uint_as_float(sq[i]) : -INFINITY);
+              for (int i = 0; i < 16; ++i) {
+                if (i >= tail) s[16 * qi + i] = 0xff800000u;   // padded keys -> -inf
+                m_tile = fmaxf(m_tile, __uint_as_float(s[16 * qi + i]));
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 16; i += 2)
-                m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(sq[i]), __uint_as_float(sq[i + 1])));
+                m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(s[16 * qi + i]), __uint_as_float(s[16 * qi + i + 1])));
             }
           }
         }
+#else
+        // ---- pass 1: row maximum straight from TMEM, one 16-key quarter at a time (a whole 64-column score row plus
+        //      the exp / pack temporaries does not fit the 96 registers a two-CTA-per-SM softmax thread has; TMEM reads
+        //      are cheap, so pass 2 simply loads the quarters again).  Padded keys of the last quarter -> -inf. ----
+        float m_tile = -INFINITY;
+#pragma unroll 1
+        for (int qi = 0; qi < nq; ++qi) {   // rolled on purpose: two resident CTAs share the instruction cache
+          uint32_t sq[16];
+          tmem_ld_32x32b_x16(ts + uint32_t(16 * qi), sq);
+          tmem_wait_ld();
+          if (tail != 0 && qi == nq - 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m_tile = fmaxf(m_tile, (i < tail) ? __uint_as_float(sq[i]) : -INFINITY);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2)
+              m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(sq[i]), __uint_as_float(sq[i + 1])));
+          }
+        }
+#endif
         // Lazy rescaling: the running maximum is only advanced (and O_t rescaled) when some row of this warp saw its
         // maximum grow by more than 2^kLazyLog2; otherwise the stale maximum keeps being the reference — P may then
         // exceed 1 (by at most 2^kLazyLog2, harmless in fp32 / bf16) and O / l at the end is unchanged mathematically.
@@ -354,12 +385,45 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           __syncwarp();
           store_pending = false;
         }
-        // ---- pass 2: P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V) ----
+#if MT_ATTN_ONE_PASS
         uint64_t l2 = pack_f32x2(0.f, 0.f);   // two partial row sums (even / odd keys), packed fp32x2 adds
         const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
 #pragma unroll
         for (int qi = 0; qi < 4; ++qi) {
           if (qi < nq) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {  // two 16-byte groups (8 keys each) per 16-key quarter
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float a0, a1;
+                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[16 * qi + 8 * g + 2 * i]),
+                                                  __uint_as_float(s[16 * qi + 8 * g + 2 * i + 1])), c2, nmc2), a0, a1);
+                float e0 = ex2_approx(a0);
+                float e1 = ex2_approx(a1);
+                l2 = add_f32x2(l2, pack_f32x2(e0, e1));
+                if (p.drop_thresh != 0u) {
+                  const uint32_t kidx = drop_row + uint32_t(j * kAtBN + 16 * qi + 8 * g + 2 * i);
+                  if (!attn_keep(bh_seed, kidx, p.drop_thresh)) e0 = 0.f;
+                  if (!attn_keep(bh_seed, kidx + 1u, p.drop_thresh)) e1 = 0.f;
+                }
+                pk[i] = pack_bf16x2(e0, e1);
+              }
+              const uint32_t chunk16 = uint32_t(2 * qi + g);
+              const uint32_t addr = prow + ((chunk16 ^ swz) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                           "r"(pk[3])
+                           : "memory");
+            }
+          }
+        }
+#else
+        // ---- pass 2: P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V) ----
+        uint64_t l2 = pack_f32x2(0.f, 0.f);   // two partial row sums (even / odd keys), packed fp32x2 adds
+        const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+#pragma unroll 1
+        for (int qi = 0; qi < nq; ++qi) {
+          {
             uint32_t sq[16];
             tmem_ld_32x32b_x16(ts + uint32_t(16 * qi), sq);
             tmem_wait_ld();
@@ -400,6 +464,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
           }
         }
+#endif
         float l_lo, l_hi;
         unpack_f32x2(l2, l_lo, l_hi);
         l_run = fmaf(l_run, alpha, l_lo + l_hi);

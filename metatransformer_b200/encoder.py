@@ -35,8 +35,14 @@ def build_encoder(scale: str = "base", **overrides) -> nn.Sequential:
 class FusedEncoder(nn.Module):
     """Runs a Sequential of `Block`s through the C-ABI whole-encoder driver (inference / frozen-encoder forward)."""
 
-    def __init__(self, blocks: nn.Sequential, fold_layernorm: bool = True, use_cuda_graph: bool = False):
+    def __init__(self, blocks: nn.Sequential, fold_layernorm: bool = True, use_cuda_graph: bool = False,
+                 precision: str = "auto"):
         super().__init__()
+        if precision not in ("auto", "bf16", "fp32"):
+            raise ValueError("FusedEncoder: precision must be 'auto', 'bf16' or 'fp32'")
+        # "auto" follows the reference's dtype rules (see Block.precision): fp32 tensors outside torch.autocast take the
+        # fp32-accurate path (3xTF32 GEMMs, 1e-4 gate), everything else the bf16 tensor-core path (1e-2 gate)
+        self.precision = precision
         self.fold_layernorm = fold_layernorm
         # replay the 84 / 168 launches of one forward from a captured CUDA graph (keyed by the buffers involved);
         # only pays off when the caller re-uses its input / output buffers
@@ -129,9 +135,20 @@ class FusedEncoder(nn.Module):
                 getattr(b, "_is_stochastic", lambda: False)() for b in self.blocks):
             raise NotImplementedError("FusedEncoder: dropout / drop-path in training mode is not supported; call the "
                                       "Blocks (nn.Sequential) for training")
+        B, N, C = x.shape
+        if self.precision == "fp32" or (self.precision == "auto" and x.dtype == torch.float32
+                                        and not torch.is_autocast_enabled()):
+            x2 = x.reshape(-1, C).float()
+            x2 = x2 if x2.is_contiguous() else x2.contiguous()
+            for blk in self.blocks:
+                x2 = blk._forward_fp32(x2, B, N)
+            y = x2.view(B, N, C)
+            if out is not None:
+                out.copy_(y)
+                return out
+            return y if x.dtype == torch.float32 else ops.cast(y, x.dtype)
         self._ensure_handle()
         lib = _lib.load()
-        B, N, C = x.shape
         if C != self.dim:
             raise ValueError(f"FusedEncoder: expected last dim {self.dim}, got {C}")
         xin = x.contiguous()

@@ -469,3 +469,64 @@ def embed_sum(table: torch.Tensor, idx: torch.Tensor, offsets: Optional[torch.Te
                                        0 if pos is None else pos.shape[0], out.data_ptr(), _DT[out_dtype], rows, d, _stream()),
               "mt_embed_sum")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp32-accuracy path (3xTF32 tensor-core GEMMs on (big, small) fp32 pairs; see csrc/mt_fp32.cu)
+# ------------------------------------------------------------------------------------------------------------------
+def _f32(*tensors):
+    _require_cuda(*tensors)
+    if any(t is not None and t.dtype != torch.float32 for t in tensors):
+        raise ValueError("fp32 path: fp32 tensors only")
+
+
+def split_tf32(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> (big, small): big = x with the low 13 mantissa bits cleared (exact in TF32), small = x - big."""
+    _f32(x)
+    big, small = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_split_tf32(x.data_ptr(), big.data_ptr(), small.data_ptr(), x.numel(), _stream()), "mt_split_tf32")
+    return big, small
+
+
+def layernorm_f32_split(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5):
+    """LayerNorm of fp32 x [M,d] in fp32 -> (big, small) pair for gemm_f32x3."""
+    _f32(x, weight, bias)
+    M, d = x.shape
+    big, small = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_layernorm_f32_split(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), big.data_ptr(),
+                                                 small.data_ptr(), M, d, float(eps), _stream()), "mt_layernorm_f32_split")
+    return big, small
+
+
+def gemm_f32x3(x_big: torch.Tensor, x_small: torch.Tensor, w_big: torch.Tensor, w_small: torch.Tensor,
+               bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, gelu: bool = False,
+               split_out: bool = False):
+    """fp32-accurate y = act(x @ w.T + bias) (+ residual) from (big, small) operand pairs; returns fp32 y, or its
+    (big, small) pair when split_out."""
+    _f32(x_big, x_small, w_big, w_small, bias, residual)
+    M, K = x_big.shape
+    N = w_big.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x_big.device)
+    ys = torch.empty_like(y) if split_out else None
+    with torch.cuda.device(x_big.device):
+        check(_lib.load().mt_gemm_f32x3(x_big.data_ptr(), x_small.data_ptr(), w_big.data_ptr(), w_small.data_ptr(), _ptr(bias),
+                                        _ptr(residual), y.data_ptr(), _ptr(ys), M, N, K, 1 if gelu else 0, _stream()),
+              "mt_gemm_f32x3")
+    return (y, ys) if split_out else y
+
+
+def attention_f32(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None):
+    """fp32 attention core on qkv [B,N,3*H*dh] -> (big, small) pair of the [B,N,H*dh] output."""
+    _f32(qkv)
+    B, N, C3 = qkv.shape
+    dh = C3 // (3 * num_heads)
+    if scale is None:
+        scale = dh ** -0.5
+    ob = torch.empty((B, N, num_heads * dh), dtype=torch.float32, device=qkv.device)
+    os_ = torch.empty_like(ob)
+    with torch.cuda.device(qkv.device):
+        check(_lib.load().mt_attention_f32(qkv.data_ptr(), ob.data_ptr(), os_.data_ptr(), B, N, num_heads, dh, float(scale),
+                                           _stream()), "mt_attention_f32")
+    return ob, os_

@@ -293,6 +293,46 @@ class Block(nn.Module):
     # statistics, the normalised activations never touch HBM.  Set to False for the plain LN-kernel + GEMM sequence.
     fold_layernorm = True
 
+    # Arithmetic of the inference forward:
+    #   "bf16": bf16 tensor-core operands, fp32 accumulation, split residual stream (1e-2 gate) — the throughput path;
+    #   "fp32": fp32-accurate 3xTF32 tensor-core GEMMs + fp32 LayerNorm / attention (1e-4 gate), ~6-8x slower;
+    #   "auto": what the reference's own dtype rules give — fp32 tensors outside torch.autocast run the fp32 path
+    #           (X-Ray/train.py:52-60), everything else (bf16 / fp16 tensors, or any tensor under autocast:
+    #           Audio/src/models/ast_models.py:145, Video/engine_for_finetuning.py:97) runs the bf16 path.
+    # Training (autograd) always uses the bf16 kernels.
+    precision = "auto"
+
+    def _use_fp32(self, x: torch.Tensor) -> bool:
+        if self.precision == "fp32":
+            return True
+        return self.precision == "auto" and x.dtype == torch.float32 and not torch.is_autocast_enabled()
+
+    def _forward_fp32(self, x2: torch.Tensor, B: int, N: int) -> torch.Tensor:
+        """fp32-accurate Block forward on an fp32 [M, C] residual stream (csrc/mt_fp32.cu)."""
+        attn, mlp = self.attn, self.mlp
+
+        def pair(mod, name, w):
+            return _cached(mod, "f32pair." + name, (w,), lambda: ops.split_tf32(w.detach().float().contiguous()))
+
+        def vec(mod, name, v):
+            return _packed(mod, name, v, torch.float32)
+
+        hb, hs = ops.layernorm_f32_split(x2, vec(self, "norm1.weight", self.norm1.weight),
+                                         vec(self, "norm1.bias", self.norm1.bias), self.norm1.eps)
+        wqb, wqs = pair(attn, "qkv", attn.qkv.weight)
+        qkv = ops.gemm_f32x3(hb, hs, wqb, wqs, bias=vec(attn, "qkv.bias", attn.qkv.bias))
+        ob, os_ = ops.attention_f32(qkv.view(B, N, -1), attn.num_heads, attn.scale)
+        wpb, wps = pair(attn, "proj", attn.proj.weight)
+        C = x2.shape[1]
+        x_mid = ops.gemm_f32x3(ob.view(B * N, C), os_.view(B * N, C), wpb, wps, bias=vec(attn, "proj.bias", attn.proj.bias),
+                               residual=x2)
+        hb, hs = ops.layernorm_f32_split(x_mid, vec(self, "norm2.weight", self.norm2.weight),
+                                         vec(self, "norm2.bias", self.norm2.bias), self.norm2.eps)
+        w1b, w1s = pair(mlp, "fc1", mlp.fc1.weight)
+        hidb, hids = ops.gemm_f32x3(hb, hs, w1b, w1s, bias=vec(mlp, "fc1.bias", mlp.fc1.bias), gelu=True, split_out=True)
+        w2b, w2s = pair(mlp, "fc2", mlp.fc2.weight)
+        return ops.gemm_f32x3(hidb, hids, w2b, w2s, bias=vec(mlp, "fc2.bias", mlp.fc2.bias), residual=x_mid)
+
     def _folded(self, name: str, lin: nn.Linear, norm: nn.LayerNorm):
         """(W*gamma bf16, colsum, b + W beta) for Linear(LayerNorm(.)); cached like `_packed`."""
         cache = self.__dict__.setdefault("_mt_pack_cache", {})
@@ -525,6 +565,10 @@ class Block(nn.Module):
         B, N, C = x.shape
         if self._is_stochastic():                               # train mode without autograd: masks still apply
             return _from_bf16(self._forward_train(_to_bf16_2d(x), B, N)[0], x)
+        if self._use_fp32(x):
+            x2 = x.reshape(-1, C).float()
+            y = self._forward_fp32(x2 if x2.is_contiguous() else x2.contiguous(), B, N).view(B, N, C)
+            return y if x.dtype == torch.float32 else ops.cast(y, x.dtype)
         if x.dtype == torch.float32 and self.fold_layernorm and x.numel() % 4 == 0:
             # fp32 caller (autocast-style: fp32 residual stream, bf16 tensor-core operands): the stream enters and leaves
             # the Block as a split hi + lo pair, so a Sequential of Blocks accumulates its 2L residual adds in fp32

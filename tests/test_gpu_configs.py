@@ -77,11 +77,14 @@ def test_full_depth_encoder_every_baseline_shape(mt, scale, B, N):
         y = fused(x.cuda().bfloat16())
         assert y.dtype == torch.bfloat16
         _gate(y, refs, f"{scale} x{depth} N={N} fused, bf16 tokens")
-        y32 = fused(x.cuda())
-        assert y32.dtype == torch.float32
-        _gate(y32, refs, f"{scale} x{depth} N={N} fused, fp32 tokens")
-        if N <= 512:
-            _gate(enc(x.cuda()), refs, f"{scale} x{depth} N={N} per-Block modules, fp32 tokens")
+        # fp32 tokens under autocast — how the reference's audio / video forks call the encoder (ast_models.py:145,
+        # engine_for_finetuning.py:97): fp32 residual stream in and out, bf16 tensor-core operands in between
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y32 = fused(x.cuda())
+            assert y32.dtype == torch.float32
+            _gate(y32, refs, f"{scale} x{depth} N={N} fused, fp32 tokens under autocast")
+            if N <= 512:
+                _gate(enc(x.cuda()), refs, f"{scale} x{depth} N={N} per-Block modules, fp32 tokens under autocast")
 
 
 def test_c4_audio_tokenizer_into_base_encoder(mt):
@@ -93,7 +96,7 @@ def test_c4_audio_tokenizer_into_base_encoder(mt):
     fbank = torch.randn(2, 1024, 128, generator=g)
     spec = orc.audio_input_prep(fbank)
     w, b = tok.proj.weight.detach().cpu(), tok.proj.bias.detach().cpu()
-    with torch.no_grad():
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         t = tok(spec.cuda())
         assert t.shape == (2, 512, 768)
         y = mt.FusedEncoder(enc)(t)
@@ -113,7 +116,7 @@ def test_c5_video_tokenizer_into_large_encoder(mt):
     g = torch.Generator().manual_seed(12)
     clip = torch.randn(1, 3, 16, 224, 224, generator=g)
     w, b = tok.proj.weight.detach().cpu(), tok.proj.bias.detach().cpu()
-    with torch.no_grad():
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         t = tok(clip.cuda())
         assert t.shape == (1, 1568, 1024)
         y = mt.FusedEncoder(enc)(t)
@@ -137,7 +140,7 @@ def test_fused_driver_rows_with_mean_much_larger_than_std(mt, lo, hi):
     x = torch.randn(B, N, dim, generator=g) + off
     with torch.no_grad():
         ref = orc.encoder(x.double(), {k: v.double() for k, v in sd.items()}, depth, heads)
-        y = mt.FusedEncoder(enc)(x.cuda())
+        y = mt.FusedEncoder(enc, precision="bf16")(x.cuda())
     assert y.dtype == torch.float32
     _gate(y.cpu().double() - x.double(), {"oracle fp64 (branch sum y - x)": ref - x.double()},
           f"mean>>std rows (|offset| in [{lo},{hi}]), fused x{depth}")
@@ -182,3 +185,64 @@ def test_split_stream_residual_gemm_and_row_statistics(mt):
         var = (m2_i.sum(-1) + (n_i * (mean_i - mean[:, None]) ** 2).sum(-1)) / N
         assert (mean - ref.mean(-1)).abs().max() < 1e-3
         assert ((var - ref.var(-1, unbiased=False)).abs() / ref.var(-1, unbiased=False)).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32-accuracy path (plain-fp32 callers, X-Ray/train.py:52-60): gate 1e-4 on BOTH metrics
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,gelu,resid,split", [(300, 768, 768, False, True, False), (197, 3072, 768, True, False, True),
+                                                    (128, 96, 40, False, False, False), (513, 768, 3072, False, True, False)])
+def test_gemm_f32x3_matches_fp64(mt, M, N, K, gelu, resid, split):
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g) * 2
+    w = torch.randn(N, K, generator=g) * 0.05
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g) if resid else None
+    ref = x.double() @ w.double().t() + b.double()
+    if gelu:
+        ref = orc.gelu_erf(ref)
+    if resid:
+        ref = ref + r.double()
+    xb, xs = mt.ops.split_tf32(x.cuda())
+    wb, ws = mt.ops.split_tf32(w.cuda())
+    assert torch.equal((xb + xs).cpu(), x)                        # the split is exact
+    y = mt.ops.gemm_f32x3(xb, xs, wb, ws, bias=b.cuda(), residual=None if r is None else r.cuda(), gelu=gelu, split_out=split)
+    if split:
+        assert torch.equal((y[0].view(torch.int32) & 0x1FFF), torch.zeros_like(y[0], dtype=torch.int32))
+        y = y[0] + y[1]
+    err = (y.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-6, f"3xTF32 GEMM {M}x{N}x{K}: max rel err {err:.2e}"
+
+
+@pytest.mark.parametrize("B,N,H,dh", [(2, 196, 3, 64), (1, 300, 2, 64), (2, 50, 4, 24), (1, 17, 2, 32)])
+def test_attention_and_layernorm_f32(mt, B, N, H, dh):
+    g = torch.Generator().manual_seed(N + dh)
+    C = H * dh
+    qkv = torch.randn(B, N, 3 * C, generator=g)
+    q, k, v = qkv.double().reshape(B, N, 3, H, dh).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = (((q @ k.transpose(-2, -1)) * dh ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+    ob, os_ = mt.ops.attention_f32(qkv.cuda(), H)
+    err = ((ob + os_).double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-6, f"fp32 attention: {err:.2e}"
+    x = torch.randn(B * N, C, generator=g) * 3 + 1.5
+    w, b = 1 + torch.randn(C, generator=g) * 0.2, torch.randn(C, generator=g) * 0.2
+    hb, hs = mt.ops.layernorm_f32_split(x.cuda(), w.cuda(), b.cuda(), 1e-5)
+    ref = orc.layer_norm(x.double(), w.double(), b.double(), 1e-5)
+    assert ((hb + hs).double().cpu() - ref).abs().max().item() < 5e-6 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("scale,B,N", [("base", 2, 196), ("large", 1, 256)])
+def test_fp32_path_full_depth_gate_1e_4(mt, scale, B, N):
+    """fp32 tokens outside autocast select the fp32-accurate path automatically (per-Block modules and FusedEncoder);
+    full depth, fp64 oracle on the unrounded weights, gate 1e-4 on rel-L2 and on max-abs / max|ref|."""
+    enc, sd, sd16, dim, heads, depth = _encoder(mt, scale, seed=13)
+    x = orc.make_tokens(B, N, dim, seed=5)
+    with torch.no_grad():
+        ref = orc.encoder(x.double(), {k: v.double() for k, v in sd.items()}, depth, heads)
+        y = enc(x.cuda())
+        yf = mt.FusedEncoder(enc)(x.cuda())
+        yb = mt.FusedEncoder(enc, precision="bf16")(x.cuda())
+    assert y.dtype == torch.float32 and torch.equal(y, yf)
+    _gate(y, {"oracle fp64": ref}, f"{scale} x{depth} N={N} fp32 path", rel=1e-4, mx=1e-4)
+    r_bf16, _ = _errs(yb, ref)
+    assert r_bf16 > 5e-4                      # precision="bf16" really is the other path
