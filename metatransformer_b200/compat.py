@@ -44,5 +44,5 @@ def install(force_timm: bool = False) -> None:
                             "timm.models.vision_transformer": vision_transformer})
     # `from Data2Seq import Data2Seq` (reference scripts run with Data2Seq/ on sys.path, Data2Seq.py:9-15)
     sys.modules.setdefault("Data2Seq", importlib.import_module(data2seq.__name__ + ".Data2Seq"))
-    for name in ("Image", "Video", "Acoustic", "Time_Series", "Hyper_Spectrum", "Text"):
+    for name in ("Image", "Video", "Acoustic", "Time_Series", "Hyper_Spectrum", "Text", "Graph"):
         sys.modules.setdefault(name, getattr(data2seq, name))

@@ -15,15 +15,17 @@ are kept and the *intended* semantics implemented:
   text                     : the reference constructs a CLIPTokenizer that returns ids, not embeddings, and its padding
                              branch is dead code (Data2Seq.py:27-28,50-52); here pre-computed (B, c) sentence features
                              are zero-padded to `dim` as Text.zero_padding does (Text.py:15-19) -> (B, 1, dim)
-  graph                    : not built (ragged host-side batching + QR-based node identifiers, Graph.py:234-305; its
-                             encoder also needs key-padding masks the timm Block does not have) -> NotImplementedError
+  graph                    : Graph.GraphFeatureTokenizer with hidden_dim = dim (the shipped call leaves hidden_dim = 1,
+                             Data2Seq.py:31-32): forward(batched_data) returns the (B, 2+T, dim) tokens; the padding mask /
+                             padded index the reference also returns are available from `self.embed(batched_data)`.  The
+                             reference's own encoder loop feeds the tokens to the Blocks WITHOUT a key-padding mask
+                             (Graph/metatransformer/modules/tokengt_graph_encoder.py:330-334), so neither does this path
 """
 import torch.nn as nn
 
-from . import Acoustic, Hyper_Spectrum, Image, Text, Time_Series, Video
+from . import Acoustic, Graph, Hyper_Spectrum, Image, Text, Time_Series, Video
 
 _IMAGE_LIKE = ('image', 'infrared', 'x-ray')
-_NEXT = ('graph',)
 
 
 class Data2Seq(nn.Module):
@@ -44,9 +46,13 @@ class Data2Seq(nn.Module):
             self.embed = Time_Series.DataEmbedding(c_in=1, d_model=self.embed_dim, token_dtype=token_dtype)
         elif self.modality == 'text':
             self.embed = Text.TextFeaturePad(embed_dim=self.embed_dim)
-        elif self.modality in _NEXT:
-            raise NotImplementedError(f"Data2Seq modality '{modality}' is not built on the B200 path yet "
-                                      "(SURVEY.md §8f rank 3)")
+        elif self.modality == 'graph':
+            # TokenGT's PCQM4Mv2 vocabulary (Graph/metatransformer/models/tokengt.py defaults) with hidden_dim = dim
+            self.embed = Graph.GraphFeatureTokenizer(num_atoms=512 * 9, num_edges=512 * 3, rand_node_id=False,
+                                                     rand_node_id_dim=64, orf_node_id=True, orf_node_id_dim=64,
+                                                     lap_node_id=False, lap_node_id_k=16, lap_node_id_sign_flip=False,
+                                                     lap_node_id_eig_dropout=0.0, type_id=True, hidden_dim=self.embed_dim,
+                                                     n_layers=12, token_dtype=token_dtype)
         else:
             raise ValueError(f"unknown modality '{modality}'")
 
@@ -54,4 +60,6 @@ class Data2Seq(nn.Module):
         if self.modality == 'audio':
             # (B, T, F) fbank -> (B, 1, F, T)   (Audio/src/models/ast_models.py:152-153)
             data = data.unsqueeze(1).transpose(2, 3)
+        if self.modality == 'graph':
+            return self.embed(data)[0]
         return self.embed(data)

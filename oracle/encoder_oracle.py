@@ -150,6 +150,37 @@ def time_series_embed(x: Tensor, conv_w: Tensor) -> Tensor:
     return tok + sinusoid_pe(T, conv_w.shape[0], x.dtype)
 
 
+def graph_tokens(sd: Dict[str, Tensor], node_data: Tensor, edge_data: Tensor, edge_index: Tensor, node_num: Sequence[int],
+                 edge_num: Sequence[int], lap_eigvec: Optional[Tensor] = None, rand_node_id: Optional[Tensor] = None,
+                 orf_node_id: Optional[Tensor] = None) -> Tensor:
+    """GraphFeatureTokenizer.forward in eval mode (Data2Seq/Graph.py:234-305) with the random node identifiers given as
+    inputs: per token  sum_f atom|edge embedding (:254-255) + rand / orf / lap encoders on [id_u ; id_v] (:263-294) +
+    order embedding of (u == v) (:296-297); sequence [graph_token, null_token, nodes, edges, zero padding] (:299-304).
+    sd = the tokenizer's state-dict.  Written per graph with plain indexing (no batched scatter)."""
+    D = sd["atom_encoder.weight"].shape[1]
+    b, T = len(node_num), max(n + e for n, e in zip(node_num, edge_num))
+    out = torch.zeros(b, T + 2, D, dtype=sd["atom_encoder.weight"].dtype)
+    n0 = e0 = 0
+    for g in range(b):
+        n, e = node_num[g], edge_num[g]
+        u = torch.cat([torch.arange(n), edge_index[0, e0:e0 + e]])
+        v = torch.cat([torch.arange(n), edge_index[1, e0:e0 + e]])
+        feat = torch.cat([sd["atom_encoder.weight"][node_data[n0:n0 + n]].sum(-2),
+                          sd["edge_encoder.weight"][edge_data[e0:e0 + e]].sum(-2)])
+        for name, ids in (("rand_encoder", rand_node_id), ("orf_encoder", orf_node_id), ("lap_encoder", lap_eigvec)):
+            if ids is not None and name + ".weight" in sd:
+                loc = ids[n0:n0 + n].to(feat.dtype)
+                k = sd[name + ".weight"].shape[1] // 2
+                loc = loc[:, :k] if loc.shape[1] >= k else torch.nn.functional.pad(loc, (0, k - loc.shape[1]))
+                feat = feat + torch.cat([loc[u], loc[v]], dim=1) @ sd[name + ".weight"].t()
+        if "order_encoder.weight" in sd:
+            feat = feat + sd["order_encoder.weight"][(u == v).long()]
+        out[g, 0], out[g, 1] = sd["graph_token.weight"][0], sd["null_token.weight"][0]
+        out[g, 2:2 + n + e] = feat
+        n0, e0 = n0 + n, e0 + e
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------
 # seeded synthetic weights (the pretrained checkpoints are external links, README.md:103-104)
 # --------------------------------------------------------------------------------------------------------------

@@ -169,6 +169,38 @@ def main():
                         w_timef_embed=de_t.temporal_embedding.embed.weight.detach().numpy())
     print("time_series_embed_mark")
 
+    # ---- Data2Seq/Graph.py GraphFeatureTokenizer (imports only torch): 3 ragged graphs, every identifier encoder on ----
+    gr_mod = _load_file_module("ref_graph", REF / "Data2Seq/Graph.py")
+    torch.manual_seed(21)
+    gt = gr_mod.GraphFeatureTokenizer(num_atoms=40, num_edges=12, rand_node_id=True, rand_node_id_dim=16, orf_node_id=True,
+                                      orf_node_id_dim=16, lap_node_id=True, lap_node_id_k=8, lap_node_id_sign_flip=False,
+                                      lap_node_id_eig_dropout=0.0, type_id=True, hidden_dim=64, n_layers=2).eval()
+    g = torch.Generator().manual_seed(23)
+    node_num, edge_num = [5, 3, 6], [8, 4, 10]
+    n_tot, e_tot = sum(node_num), sum(edge_num)
+    node_data = torch.randint(1, 40, (n_tot, 3), generator=g)
+    edge_data = torch.randint(1, 12, (e_tot, 2), generator=g)
+    edge_index = torch.cat([torch.randint(0, n, (2, e), generator=g) for n, e in zip(node_num, edge_num)], dim=1)
+    lap_eigvec = torch.randn(n_tot, 8, generator=g)
+    batch = dict(node_data=node_data, in_degree=torch.zeros(n_tot, dtype=torch.long), out_degree=torch.zeros(n_tot, dtype=torch.long),
+                 node_num=node_num, lap_eigvec=lap_eigvec, lap_eigval=torch.zeros(n_tot, 8), edge_index=edge_index,
+                 edge_data=edge_data, edge_num=edge_num)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        feat, pmask, pidx = gt(batch)
+    # the two random identifier draws of that call, replayed in the same order (Graph.py:264-281)
+    torch.manual_seed(5)
+    rid = torch.nn.functional.normalize(torch.rand(n_tot, 16), p=2, dim=1)
+    node_mask = gt.get_node_mask(node_num, torch.device("cpu"))
+    orf = gr_mod.gaussian_orthogonal_random_matrix_batched(3, max(node_num), max(node_num))[node_mask]
+    orf = torch.nn.functional.normalize(torch.nn.functional.pad(orf, (0, 16 - max(node_num)), value=0.0), p=2, dim=1)
+    np.savez_compressed(OUT / "graph_tokenizer.npz", node_data=node_data.numpy(), edge_data=edge_data.numpy(),
+                        edge_index=edge_index.numpy(), lap_eigvec=lap_eigvec.numpy(), node_num=np.array(node_num),
+                        edge_num=np.array(edge_num), rand_node_id=rid.numpy(), orf_node_id=orf.numpy(), y=feat.numpy(),
+                        padding_mask=pmask.numpy(), padded_index=pidx.numpy(),
+                        **{"sd." + k: v.numpy() for k, v in gt.state_dict().items()})
+    print("graph_tokenizer", tuple(feat.shape))
+
     # ---- AST tokenizer: the reference's PatchEmbed with the overlapping-stride conv ASTModel installs (:86) ----
     _stub_timm()
     ast_mod = _load_file_module("ref_ast_models", REF / "Audio/src/models/ast_models.py")

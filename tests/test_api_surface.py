@@ -59,8 +59,10 @@ def test_unsupported_configurations_raise():
         mt.Block(64, 1, act_layer=nn.ReLU)
     with pytest.raises(NotImplementedError):
         mt.Block(64, 1, norm_layer=nn.BatchNorm1d)
-    with pytest.raises(NotImplementedError):
-        mt.Data2Seq("graph", 768)
+    gt = mt.Data2Seq("graph", 768).embed
+    assert isinstance(gt, data2seq.Graph.GraphFeatureTokenizer) and gt.encoder_embed_dim == 768
+    assert {"atom_encoder.weight", "edge_encoder.weight", "graph_token.weight", "null_token.weight", "orf_encoder.weight",
+            "order_encoder.weight"} <= set(gt.state_dict().keys())
     assert isinstance(mt.Data2Seq("text", 768).embed, data2seq.Text.TextFeaturePad)
     with pytest.raises(NotImplementedError):
         data2seq.Text.get_text_embeddings(["a sentence"])        # the CLIP tower itself is not part of the path

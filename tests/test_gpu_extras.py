@@ -415,3 +415,36 @@ def test_standalone_droppath_and_block_pos_prologue(mt):
     out = blk(xb.cuda().requires_grad_(True), pos=posp)
     out.float().sum().backward()
     assert posp.grad is not None and posp.grad.shape == posp.shape and torch.isfinite(posp.grad).all()
+
+
+def test_graph_tokenizer_matches_reference_golden(mt, golden_dir):
+    """Data2Seq/Graph.py GraphFeatureTokenizer: three ragged graphs, every identifier encoder on; vectors produced by the
+    reference's own class on CPU, its two random node-identifier draws replayed and injected (make_golden.py)."""
+    import numpy as np
+    z = np.load(golden_dir / "graph_tokenizer.npz")
+    tok = mt.data2seq.Graph.GraphFeatureTokenizer(num_atoms=40, num_edges=12, rand_node_id=True, rand_node_id_dim=16,
+                                                  orf_node_id=True, orf_node_id_dim=16, lap_node_id=True, lap_node_id_k=8,
+                                                  lap_node_id_sign_flip=False, lap_node_id_eig_dropout=0.0, type_id=True,
+                                                  hidden_dim=64, n_layers=2)
+    tok.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    tok = tok.cuda().eval()
+    batch = dict(node_data=torch.from_numpy(z["node_data"]).cuda(), edge_data=torch.from_numpy(z["edge_data"]).cuda(),
+                 edge_index=torch.from_numpy(z["edge_index"]).cuda(), lap_eigvec=torch.from_numpy(z["lap_eigvec"]).cuda(),
+                 node_num=z["node_num"].tolist(), edge_num=z["edge_num"].tolist())
+    with torch.no_grad():
+        feat, pmask, pidx = tok(batch, rand_node_id=torch.from_numpy(z["rand_node_id"]).cuda(),
+                                orf_node_id=torch.from_numpy(z["orf_node_id"]).cuda())
+    assert torch.equal(pmask.cpu(), torch.from_numpy(z["padding_mask"])) and torch.equal(pidx.cpu(), torch.from_numpy(z["padded_index"]))
+    _assert_close(feat, torch.from_numpy(z["y"]), what="GraphFeatureTokenizer golden")
+    assert float(feat[pmask].abs().max()) == 0.0                     # padding tokens are exactly zero
+    # the dispatcher + the Graph fork's Block geometry (768 wide, 32 heads) on the tokens
+    d2s = mt.Data2Seq("graph", 768).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    nn_, en_ = [6, 4], [9, 5]
+    gb = dict(node_data=torch.randint(1, 4000, (10, 9), generator=g).cuda(), edge_data=torch.randint(1, 1000, (14, 3), generator=g).cuda(),
+              edge_index=torch.cat([torch.randint(0, n, (2, e), generator=g) for n, e in zip(nn_, en_)], dim=1).cuda(),
+              node_num=nn_, edge_num=en_)
+    with torch.no_grad():
+        t = d2s(gb)
+        y = mt.Block(dim=768, num_heads=32, qkv_bias=True).cuda().eval()(t)
+    assert t.shape == (2, 2 + 15, 768) and y.shape == t.shape and torch.isfinite(y).all()

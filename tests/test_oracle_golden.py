@@ -121,3 +121,16 @@ def test_oracle_vs_torchvision_encoderblock():
         blk.mlp[3].weight.copy_(sd["0.mlp.fc2.weight"]); blk.mlp[3].bias.copy_(sd["0.mlp.fc2.bias"])
         x = orc.make_tokens(2, 19, dim)
         assert torch.allclose(orc.encoder(x, sd, 1, heads), blk(x), atol=2e-5)
+
+
+def test_graph_tokenizer_oracle_matches_reference_golden(golden_dir):
+    """The oracle's restatement of Data2Seq/Graph.py:234-305 reproduces the reference's own output, given the two random
+    node-identifier draws the generator script replayed (tests/golden/make_golden.py)."""
+    import numpy as np
+    z = np.load(golden_dir / "graph_tokenizer.npz")
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    y = orc.graph_tokens(sd, torch.from_numpy(z["node_data"]), torch.from_numpy(z["edge_data"]), torch.from_numpy(z["edge_index"]),
+                         z["node_num"].tolist(), z["edge_num"].tolist(), torch.from_numpy(z["lap_eigvec"]),
+                         torch.from_numpy(z["rand_node_id"]), torch.from_numpy(z["orf_node_id"]))
+    ref = torch.from_numpy(z["y"])
+    assert y.shape == ref.shape and (y - ref).abs().max().item() <= 2e-6
