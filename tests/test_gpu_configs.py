@@ -211,7 +211,7 @@ def test_gemm_f32x3_matches_fp64(mt, M, N, K, gelu, resid, split):
         assert torch.equal((y[0].view(torch.int32) & 0x1FFF), torch.zeros_like(y[0], dtype=torch.int32))
         y = y[0] + y[1]
     err = (y.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
-    assert err < 2e-5, f"3xTF32 GEMM {M}x{N}x{K}: max rel err {err:.2e}"      # 2^-21 operand error x sqrt(K) growth
+    assert err < 6e-5, f"3xTF32 GEMM {M}x{N}x{K}: max rel err {err:.2e}"      # ~2^-21 per product, fp32 accumulation over K
 
 
 @pytest.mark.parametrize("B,N,H,dh", [(2, 196, 3, 64), (1, 300, 2, 64), (2, 50, 4, 24), (1, 17, 2, 32)])
