@@ -85,20 +85,33 @@ im2row_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const
 }
 
 // Vector path without per-element index arithmetic (ncu, round 2: the kernel above was issue-bound at 73 % issue-slot
-// utilisation / 57 % of DRAM peak — six integer divisions per 16-byte store).  A block walks a contiguous run of kRun
-// tokens: the thread's K offsets (which 8-pixel segment of which (c, dt, dh) row) do not depend on the token and are
-// decoded once per thread, the token coordinates are decoded once per run and then advanced incrementally.
-constexpr int kRun = 32;         // tokens per block iteration
+// utilisation / 57 % of DRAM peak — six integer divisions per 16-byte store).  A 256-thread block is laid out as
+// rpb token rows x tpr K-segments (tpr = min(K/8, 256)); a thread's K offset (which 8-pixel segment of which (c, dt, dh)
+// row) does not depend on the token and is decoded once, the token coordinates are decoded once per run and then advanced
+// incrementally; four tokens are in flight per thread (eight 16-byte loads) before the first store.
+constexpr int kRun = 64;         // tokens per block iteration and token row of the block
 constexpr int kMaxSeg = 4;       // 8-element K segments per thread (K <= 8192)
+
+struct TokenPos { int b, tp, hp, wp; };
+MT_DEVINL void token_advance(TokenPos& t, int step, const Im2RowParams& p) {
+  t.wp += step;
+  while (t.wp >= p.Wp) {
+    t.wp -= p.Wp;
+    if (++t.hp == p.Hp) { t.hp = 0; if (++t.tp == p.Tp) { t.tp = 0; ++t.b; } }
+  }
+}
 
 template <typename TIn>
 __global__ void __launch_bounds__(256)
-im2row_run_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const Im2RowParams p) {
+im2row_run_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const Im2RowParams p, int tpr, int rpb) {
   const int k8_per_row = p.K >> 3;
+  const int rl = int(threadIdx.x) / tpr;        // token row of this thread inside the block
+  const int kt0 = int(threadIdx.x) - rl * tpr;  // its first K segment
+  if (rl >= rpb) return;
   long long koff[kMaxSeg];
 #pragma unroll
   for (int i = 0; i < kMaxSeg; ++i) {
-    int kk = (int(threadIdx.x) + 256 * i) << 3;
+    int kk = (kt0 + tpr * i) << 3;
     const int dw0 = kk % p.kw; kk /= p.kw;
     const int dh = kk % p.kh; kk /= p.kh;
     const int dt = kk % p.kt;
@@ -106,34 +119,46 @@ im2row_run_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, c
     koff[i] = ((long long)(c * p.T + dt) * p.H + dh) * p.W + dw0;
   }
   const long long plane = (long long)p.H * p.W;
+  const int nseg = (k8_per_row + tpr - 1) / tpr;
   for (long long m0 = (long long)blockIdx.x * kRun; m0 < p.M; m0 += (long long)gridDim.x * kRun) {
-    long long r = m0;
-    int wp = int(r % p.Wp); r /= p.Wp;
-    int hp = int(r % p.Hp); r /= p.Hp;
-    int tp = int(r % p.Tp);
-    int b = int(r / p.Tp);
-    const int run = int(min((long long)kRun, p.M - m0));
-    for (int t = 0; t < run; ++t) {
-      const long long base = ((long long)b * p.C * p.T + (long long)tp * p.st) * plane + (long long)(hp * p.sh) * p.W + wp * p.sw;
-      __nv_bfloat16* dst = rows + size_t(m0 + t) * p.K;
+    long long r = m0 + rl;
+    TokenPos tk;
+    tk.wp = int(r % p.Wp); r /= p.Wp;
+    tk.hp = int(r % p.Hp); r /= p.Hp;
+    tk.tp = int(r % p.Tp);
+    tk.b = int(r / p.Tp);
+    const long long m_end = min(m0 + (long long)kRun, p.M);
+    for (long long m = m0 + rl; m < m_end; m += 4LL * rpb) {
+      long long base[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ok[u] = (m + (long long)u * rpb) < m_end;
+        base[u] = ((long long)tk.b * p.C * p.T + (long long)tk.tp * p.st) * plane + (long long)(tk.hp * p.sh) * p.W + tk.wp * p.sw;
+        token_advance(tk, rpb, p);
+      }
 #pragma unroll
       for (int i = 0; i < kMaxSeg; ++i) {
-        const int k8 = int(threadIdx.x) + 256 * i;
-        if (k8 < k8_per_row) {
-          uint4 o;
+        const int k8 = kt0 + tpr * i;
+        if (i >= nseg || k8 >= k8_per_row) continue;
+        uint4 o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
           if constexpr (sizeof(TIn) == 4) {
-            const float4* src = reinterpret_cast<const float4*>(x + base + koff[i]);
+            const float4* src = reinterpret_cast<const float4*>(x + base[u] + koff[i]);
             const float4 a = __ldg(src);
             const float4 c4 = __ldg(src + 1);
-            o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-            o.z = pack_bf16x2(c4.x, c4.y); o.w = pack_bf16x2(c4.z, c4.w);
+            o[u].x = pack_bf16x2(a.x, a.y); o[u].y = pack_bf16x2(a.z, a.w);
+            o[u].z = pack_bf16x2(c4.x, c4.y); o[u].w = pack_bf16x2(c4.z, c4.w);
           } else {
-            o = __ldg(reinterpret_cast<const uint4*>(x + base + koff[i]));
+            o[u] = __ldg(reinterpret_cast<const uint4*>(x + base[u] + koff[i]));
           }
-          *reinterpret_cast<uint4*>(dst + (k8 << 3)) = o;
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ok[u]) *reinterpret_cast<uint4*>(rows + size_t(m + (long long)u * rpb) * p.K + (k8 << 3)) = o[u];
       }
-      if (++wp == p.Wp) { wp = 0; if (++hp == p.Hp) { hp = 0; if (++tp == p.Tp) { tp = 0; ++b; } } }
     }
   }
 }
@@ -155,9 +180,12 @@ static int launch_im2row(const void* x, void* rows, const Im2RowParams& p, cudaS
   const TIn* xp = reinterpret_cast<const TIn*>(x);
   __nv_bfloat16* rp = reinterpret_cast<__nv_bfloat16*>(rows);
   if (vec && (p.K >> 3) <= 256 * kMaxSeg) {
+    const int k8 = p.K >> 3;
+    const int tpr = k8 < 256 ? k8 : 256;
+    const int rpb = 256 / tpr;
     long long runs = (p.M + kRun - 1) / kRun;
     long long rblocks = runs < (long long)sms * 16 ? runs : (long long)sms * 16;
-    im2row_run_kernel<TIn><<<unsigned(rblocks), 256, 0, s>>>(xp, rp, p);
+    im2row_run_kernel<TIn><<<unsigned(rblocks), 256, 0, s>>>(xp, rp, p, tpr, rpb);
   } else if (vec) im2row_kernel<TIn, true><<<unsigned(blocks), 256, 0, s>>>(xp, rp, p);
   else im2row_kernel<TIn, false><<<unsigned(blocks), 256, 0, s>>>(xp, rp, p);
   MT_CHECK_CUDA(cudaGetLastError());
