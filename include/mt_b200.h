@@ -115,6 +115,15 @@ int mt_gemm_bf16_splitk(const void* x, const void* w, float* y_f32, int M, int N
  * Autograd of nn.Linear.weight in fine-tune mode (Audio/src/traintest.py:126-143) and of the conv tokenizers.       */
 int mt_gemm_bf16_wgrad(const void* dy, const void* x, float* dw_f32, int T, int N_out, int K_in, int splits, void* stream);
 
+/* ---- fp8 (e4m3) opt-in Linear --------------------------------------------------------------
+ * mt_quantize_fp8: q[i] = sat_e4m3(x[i] / scale) (per-tensor scale; x bf16, n % 8 == 0).
+ * mt_gemm_fp8:     y = act(scale * (xq @ wq^T) + bias) (+ residual); xq [M,K] / wq [N,K] e4m3 bytes, K % 16 == 0,
+ *                  scale = scale_x * scale_w, bias fp32, residual / y bf16.  tcgen05.mma.kind::f8f6f4, fp32 accumulation.
+ * An inference option for callers that own a calibration (the reference has none); the encoder driver does not use it. */
+int mt_quantize_fp8(const void* src_bf16, void* dst_e4m3, size_t n, float scale, void* stream);
+int mt_gemm_fp8(const void* xq, const void* wq, const float* bias, const void* residual, void* y, int M, int N, int K, int act,
+                float scale, void* stream);
+
 /* ---- E2: LayerNorm over the last dim, fp32 statistics, biased variance -------------------------------------
  * y[M,d] (bf16) = (x - mean) * rsqrt(var + eps) * gamma + beta;  x bf16 or fp32 (x_dtype), gamma/beta fp32.
  * Replaces norm1 / norm2 = nn.LayerNorm(d) of Block (attention.py:46,50; eps 1e-5 per README.md:131).       */

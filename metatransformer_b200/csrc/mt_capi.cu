@@ -149,6 +149,24 @@ __global__ void scale_kernel(T* __restrict__ p, size_t n, float s) {
   }
 }
 
+// per-tensor fp8 (e4m3) quantisation: q = sat(x * inv_scale), 8 elements per thread-iteration
+__global__ void quantize_e4m3_kernel(const __nv_bfloat16* __restrict__ src, uint8_t* __restrict__ dst, size_t n, float inv_scale) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x * 8;
+  for (size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i + 7 < n; i += stride) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t out[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint16_t pr;
+      // cvt packs {first operand -> upper byte, second -> lower byte}
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(pr) : "f"(bf16_hi(w[j]) * inv_scale), "f"(bf16_lo(w[j]) * inv_scale));
+      out[j >> 1] |= uint32_t(pr) << (16 * (j & 1));
+    }
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(out[0], out[1]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // elementwise cast (weight packing fp32 -> bf16, boundary conversions). Memory-bound, 16 B per thread-load.
 // ------------------------------------------------------------------------------------------------
@@ -303,6 +321,21 @@ extern "C" int mt_allreduce(void* nccl_comm, void* buf, size_t count, int dtype,
     else scale_kernel<__nv_bfloat16><<<unsigned(blocks), 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(buf), count, scale);
     MT_CHECK_CUDA(cudaGetLastError());
   }
+  return MT_OK;
+}
+
+extern "C" int mt_quantize_fp8(const void* src_bf16, void* dst_e4m3, size_t n, float scale, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(src_bf16 && dst_e4m3, MT_ERR_BAD_SHAPE, "mt_quantize_fp8: null pointer");
+  MT_REQUIRE(n % 8 == 0 && scale > 0.f, MT_ERR_BAD_SHAPE, "mt_quantize_fp8: n %% 8 == 0 and scale > 0 required");
+  MT_REQUIRE((reinterpret_cast<uintptr_t>(src_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_e4m3) & 7) == 0, MT_ERR_BAD_ALIGN,
+             "mt_quantize_fp8: src 16-byte, dst 8-byte aligned");
+  if (n == 0) return MT_OK;
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  quantize_e4m3_kernel<<<unsigned(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src_bf16), reinterpret_cast<uint8_t*>(dst_e4m3), n, 1.0f / scale);
+  MT_CHECK_CUDA(cudaGetLastError());
   return MT_OK;
 }
 

@@ -99,6 +99,8 @@ struct GemmParams {
   int mn_major;                 // 1: both operands are stored reduction-dim-major (A = dY[k, m], B = X[k, n]: the weight
                                 // gradient dW = dY^T X straight from the row-major activations, no transposed copies)
   unsigned long long* tl;       // optional timeline slot {first CTA start, last CTA end} in globaltimer ns, or nullptr
+  int fp8;                      // operands are e4m3 bytes (kind::f8f6f4, 128 elements of K per swizzle row); generic epilogue
+  float acc_scale;              // the accumulator is multiplied by this before the bias (fp8: scale_x * scale_w; else 1)
   __nv_bfloat16* y_direct;      // != nullptr: the epilogue writes its bf16 results straight from registers (one 32-byte
   __nv_bfloat16* ylo_direct;    // sector per thread and 16-column piece) instead of staging them in shared memory for a
                                 // TMA store: the staging write + TMA read of every tile competes with the operand
@@ -219,7 +221,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   timeline_start(p.tl);
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;   // work items: (tile, K split), split fastest
-  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int kbk = (MODE == kEpiGeneric && p.fp8) ? 2 * kBK : kBK;      // elements of K per 128-byte swizzle row
+  const int num_kb = (p.K + kbk - 1) / kbk;
 
   // register re-distribution (compiled for 96 / thread): the four role warps need almost nothing, the residual epilogue
   // holds a whole tile's worth of prefetched residual (hi) per thread
@@ -268,12 +271,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             // the leader's expect_tx of the same phase (tx-count goes transiently negative, which is legal); it can
             // never land in a later phase because the peer only re-uses a slot after the leader's MMA consumed it.
             if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg::kStageBytes);
-            tma_load_2d_cg2(sa, &tm_a, fb, kb * kBK, row_a, kEvictNormal);
-            tma_load_2d_cg2(sb, &tm_b, fb, kb * kBK, row_b, kEvictLast);
+            tma_load_2d_cg2(sa, &tm_a, fb, kb * kbk, row_a, kEvictNormal);
+            tma_load_2d_cg2(sb, &tm_b, fb, kb * kbk, row_b, kEvictLast);
           } else {
             mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-            tma_load_2d(sa, &tm_a, full_bar(stage), kb * kBK, row_a, kEvictNormal);
-            tma_load_2d(sb, &tm_b, full_bar(stage), kb * kBK, row_b, kEvictLast);
+            tma_load_2d(sa, &tm_a, full_bar(stage), kb * kbk, row_a, kEvictNormal);
+            tma_load_2d(sb, &tm_b, full_bar(stage), kb * kbk, row_b, kEvictLast);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -283,7 +286,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // =============================== MMA issuer =================================
     if (leader && lane == 0) {
       const bool mnm = (MODE == kEpiGeneric) && p.mn_major;
-      const uint32_t idesc = mnm ? make_idesc_bf16(kBM * CG, kBN, 1, 1) : make_idesc_bf16(kBM * CG, kBN);
+      const bool f8 = (MODE == kEpiGeneric) && p.fp8;
+      const uint32_t idesc = f8 ? make_idesc_e4m3(kBM * CG, kBN)
+                                : (mnm ? make_idesc_bf16(kBM * CG, kBN, 1, 1) : make_idesc_bf16(kBM * CG, kBN));
       // K step of 16: K-major = 32 B inside the swizzle row; MN-major = 16 rows of 128 B
       const uint64_t kstep = mnm ? uint64_t(2048 >> 4) : uint64_t(2);
       int stage = 0;
@@ -306,8 +311,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance 16 along K: +2 (32 B inside the 128B swizzle row) or +128 (16 rows) in the (addr >> 4) field
-            umma_f16_ss<CG>(d_tmem, adesc + kstep * uint64_t(k), bdesc + kstep * uint64_t(k), idesc,
-                            (kb > kb_begin || k > 0) ? 1u : 0u);
+            // (fp8: the same four 32-byte steps per 128-byte row, 32 elements each)
+            if (f8) umma_f8_ss<CG>(d_tmem, adesc + kstep * uint64_t(k), bdesc + kstep * uint64_t(k), idesc,
+                                   (kb > kb_begin || k > 0) ? 1u : 0u);
+            else umma_f16_ss<CG>(d_tmem, adesc + kstep * uint64_t(k), bdesc + kstep * uint64_t(k), idesc,
+                                 (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           if constexpr (CG == 2) umma_commit_cg2_mc(empty_bar(stage), 0x3);
           else umma_commit(empty_bar(stage));
@@ -415,6 +423,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       bias_pf = load_bias(t + num_clusters);
       stat_pf = load_stat(t + num_clusters);
       const uint64_t ln_rstd2 = pack_f32x2(ln_rstd, ln_rstd), ln_nmr2 = pack_f32x2(ln_nmr, ln_nmr);
+      const float acc_scale = kGen ? p.acc_scale : 1.0f;
+      const uint64_t acc_scale2 = pack_f32x2(acc_scale, acc_scale);
       uint64_t roff2 = pack_f32x2(0.f, 0.f);
       if constexpr (kHiLo) {
         if (p.row_offset != nullptr && row < p.M) {
@@ -531,8 +541,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               v01 = fma_f32x2(v01, ln_rstd2, fma_f32x2(ln_nmr2, pack_f32x2(c4.x, c4.y), pack_f32x2(b4.x, b4.y)));
               v23 = fma_f32x2(v23, ln_rstd2, fma_f32x2(ln_nmr2, pack_f32x2(c4.z, c4.w), pack_f32x2(b4.z, b4.w)));
             } else {
-              v01 = add_f32x2(v01, pack_f32x2(b4.x, b4.y));
-              v23 = add_f32x2(v23, pack_f32x2(b4.z, b4.w));
+              v01 = fma_f32x2(v01, acc_scale2, pack_f32x2(b4.x, b4.y));
+              v23 = fma_f32x2(v23, acc_scale2, pack_f32x2(b4.z, b4.w));
             }
             if (do_gelu) {
               v01 = gelu_erf_x2(v01);
@@ -678,6 +688,7 @@ struct GemmCall {
   float* out_row_sums;
   float* out_f32; int split_k; int resid_period; int mn_major;
   const float* row_offset;
+  int fp8; float acc_scale;
 };
 
 template <int CG, int MODE>
@@ -698,18 +709,22 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w, dims_b, str_b, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   } else {
+    // K-major operands: 128-byte swizzle rows = 64 bf16 or 128 fp8 elements of K
+    const CUtensorMapDataType dt = c.fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const uint64_t esz = c.fp8 ? 1 : 2;
+    const uint32_t kbox = c.fp8 ? 2 * kBK : kBK;
     {
       uint64_t dims[2] = {uint64_t(K), uint64_t(M)};
-      uint64_t strides[1] = {uint64_t(K) * 2};
-      uint32_t box[2] = {uint32_t(kBK), uint32_t(kBM)};
-      int rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      uint64_t strides[1] = {uint64_t(K) * esz};
+      uint32_t box[2] = {kbox, uint32_t(kBM)};
+      int rc = encode_tmap(&tm_a, dt, 2, c.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
     {
       uint64_t dims[2] = {uint64_t(K), uint64_t(N)};
-      uint64_t strides[1] = {uint64_t(K) * 2};
-      uint32_t box[2] = {uint32_t(kBK), uint32_t(Cfg::kBRows)};
-      int rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      uint64_t strides[1] = {uint64_t(K) * esz};
+      uint32_t box[2] = {kbox, uint32_t(Cfg::kBRows)};
+      int rc = encode_tmap(&tm_b, dt, 2, c.w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
   }
@@ -745,6 +760,8 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   p.has_out_lo = c.y_lo != nullptr ? 1 : 0;
   p.row_offset = c.row_offset;
   p.out_f32 = c.out_f32;
+  p.fp8 = c.fp8;
+  p.acc_scale = c.fp8 ? c.acc_scale : 1.0f;
   p.tl = timeline_next_slot();
   {
     // MT_B200_EPI_DIRECT: 1 = every bf16 output leaves the epilogue as 32-byte register stores, 0 = staged + TMA store
@@ -759,7 +776,7 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
     p.ylo_direct = ok ? reinterpret_cast<__nv_bfloat16*>(c.y_lo) : nullptr;
   }
   {
-    const int num_kb = ceil_div(K, kBK);
+    const int num_kb = ceil_div(K, c.fp8 ? 2 * kBK : kBK);
     int sk = c.split_k < 1 ? 1 : (c.split_k > num_kb ? num_kb : c.split_k);
     p.kb_per_split = ceil_div(num_kb, sk);
     p.split_k = ceil_div(num_kb, p.kb_per_split);   // every split non-empty
@@ -794,7 +811,7 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
 // picks the epilogue specialisation for a call
 template <int CG>
 static int dispatch_gemm(const GemmCall& c, cudaStream_t s) {
-  const bool special_ok = c.out_f32 == nullptr && c.act != 2 && c.resid_period == 0 && !c.mn_major;
+  const bool special_ok = c.out_f32 == nullptr && c.act != 2 && c.resid_period == 0 && !c.mn_major && !c.fp8;
   if (special_ok && c.row_stats != nullptr && c.resid == nullptr && c.out_row_sums == nullptr && c.y_lo == nullptr) {
     if (c.act == 1) return launch_gemm<CG, kEpiLnGelu>(c, s);
     return launch_gemm<CG, kEpiLn>(c, s);
@@ -953,4 +970,24 @@ extern "C" int mt_gemm_bf16_wgrad(const void* dy, const void* x, float* dw_f32, 
   GemmCall c = {};
   c.x = dy; c.w = x; c.ldr = K_in; c.M = N_out; c.N = K_in; c.K = T; c.out_f32 = dw_f32; c.split_k = splits; c.mn_major = 1;
   return launch_gemm<2, kEpiGeneric>(c, s);
+}
+
+// fp8 (e4m3) opt-in GEMM:  y = act(scale * (xq @ wq^T) + bias) (+ residual), xq / wq = e4m3 bytes
+// [M,K] / [N,K] (K-major, K % 16 == 0), scale = scale_x * scale_w of the per-tensor quantisation x ~ scale_x * xq.
+// Same pipeline as mt_gemm_bf16 (tcgen05.mma.kind::f8f6f4: twice the K per shared-memory byte, fp32 accumulation in TMEM),
+// generic epilogue, bf16 output.
+extern "C" int mt_gemm_fp8(const void* xq, const void* wq, const float* bias, const void* residual, void* y, int M, int N, int K,
+                           int act, float scale, void* stream) {
+  using namespace mt;
+  MT_REQUIRE(xq && wq && y, MT_ERR_BAD_SHAPE, "mt_gemm_fp8: null pointer");
+  MT_REQUIRE(M > 0 && N > 0 && K > 0 && K % 16 == 0 && N % 32 == 0, MT_ERR_BAD_SHAPE,
+             "mt_gemm_fp8: need M, N, K > 0, K %% 16 == 0, N %% 32 == 0 (got %d,%d,%d)", M, N, K);
+  MT_REQUIRE(act == 0 || act == 1, MT_ERR_UNSUPPORTED, "mt_gemm_fp8: act must be 0 or 1 (gelu)");
+  MT_REQUIRE(((reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(wq) | reinterpret_cast<uintptr_t>(y) |
+               reinterpret_cast<uintptr_t>(bias)) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 31) == 0,
+             MT_ERR_BAD_ALIGN, "mt_gemm_fp8: pointers must be 16-byte (residual: 32-byte) aligned");
+  GemmCall c = {};
+  c.x = xq; c.w = wq; c.bias = bias; c.resid = residual; c.ldr = N; c.y = y; c.M = M; c.N = N; c.K = K; c.act = act;
+  c.split_k = 1; c.fp8 = 1; c.acc_scale = scale;
+  return launch_gemm<2, kEpiGeneric>(c, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -200,6 +200,23 @@ MT_DEVINL void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint
         : "memory");
   }
 }
+// same with fp8 (e4m3 / e5m2, chosen in the instruction descriptor) operands: 32 elements of K per instruction
+template <int CG>
+MT_DEVINL void umma_f8_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 // tcgen05.commit: arrive on `bar` once every previously issued tcgen05.mma of this thread has finished.
 // (implies tcgen05.fence::before_thread_sync)
 MT_DEVINL void umma_commit(uint32_t bar) {
@@ -308,6 +325,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | (uint32_t(b_mn_major) << 16) // b_major
          | (uint32_t(N >> 3) << 17)     // n_dim
          | (uint32_t(M >> 4) << 24);    // m_dim
+}
+
+// Instruction descriptor for kind::f8f6f4 with e4m3 x e4m3 -> fp32 (a_format = b_format = 0), K-major operands.
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
+  return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------

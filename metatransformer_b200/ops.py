@@ -530,3 +530,32 @@ def attention_f32(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = No
         check(_lib.load().mt_attention_f32(qkv.data_ptr(), ob.data_ptr(), os_.data_ptr(), B, N, num_heads, dh, float(scale),
                                            _stream()), "mt_attention_f32")
     return ob, os_
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp8 (e4m3) opt-in Linear
+# ------------------------------------------------------------------------------------------------------------------
+def quantize_fp8(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """bf16 -> e4m3 bytes (uint8 tensor of the same shape): q = sat(x / scale), so that x ~ scale * q."""
+    _require_cuda(x)
+    if x.dtype != torch.bfloat16 or x.numel() % 8:
+        raise ValueError("quantize_fp8: bf16 tensor with numel % 8 == 0")
+    q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.load().mt_quantize_fp8(x.data_ptr(), q.data_ptr(), x.numel(), float(scale), _stream()), "mt_quantize_fp8")
+    return q
+
+
+def linear_fp8(xq: torch.Tensor, wq: torch.Tensor, scale: float, bias: Optional[torch.Tensor] = None,
+               residual: Optional[torch.Tensor] = None, gelu: bool = False) -> torch.Tensor:
+    """y (bf16) = act(scale * (xq @ wq.T) + bias) (+ residual) on e4m3 operands (uint8 tensors [M,K], [N,K])."""
+    _require_cuda(xq, wq, bias, residual)
+    if xq.dtype != torch.uint8 or wq.dtype != torch.uint8:
+        raise ValueError("linear_fp8: operands are uint8 tensors holding e4m3 bytes (see quantize_fp8)")
+    M, K = xq.shape
+    N = wq.shape[0]
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=xq.device)
+    with torch.cuda.device(xq.device):
+        check(_lib.load().mt_gemm_fp8(xq.data_ptr(), wq.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M, N, K,
+                                      1 if gelu else 0, float(scale), _stream()), "mt_gemm_fp8")
+    return y

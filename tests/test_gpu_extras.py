@@ -448,3 +448,32 @@ def test_graph_tokenizer_matches_reference_golden(mt, golden_dir):
         t = d2s(gb)
         y = mt.Block(dim=768, num_heads=32, qkv_bias=True).cuda().eval()(t)
     assert t.shape == (2, 2 + 15, 768) and y.shape == t.shape and torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize("M,N,K,gelu,resid", [(300, 768, 3072, False, True), (197, 3072, 768, True, False), (64, 96, 48, False, False)])
+def test_fp8_e4m3_linear_opt_in(mt, M, N, K, gelu, resid):
+    """mt_quantize_fp8 + mt_gemm_fp8 (tcgen05.mma.kind::f8f6f4): the quantiser agrees with torch's e4m3 cast, and the GEMM
+    is exact on the quantised operands (products of e4m3 values accumulate in fp32) up to the bf16 output rounding."""
+    g = torch.Generator().manual_seed(M + K)
+    x = _bf16_round(torch.randn(M, K, generator=g) * 2)
+    w = _bf16_round(torch.randn(N, K, generator=g) * 0.05)
+    b = torch.randn(N, generator=g) * 0.3
+    r = _bf16_round(torch.randn(M, N, generator=g)) if resid else None
+    sx, sw = float(x.abs().max()) / 448.0, float(w.abs().max()) / 448.0
+    xq = mt.ops.quantize_fp8(x.cuda().bfloat16(), sx)
+    wq = mt.ops.quantize_fp8(w.cuda().bfloat16(), sw)
+    xq_ref = (x / sx).to(torch.float8_e4m3fn)
+    assert torch.equal(xq.cpu().view(torch.float8_e4m3fn).float(), xq_ref.float())
+    xd, wd = xq.cpu().view(torch.float8_e4m3fn).double() * sx, wq.cpu().view(torch.float8_e4m3fn).double() * sw
+    ref = xd @ wd.t() + b.double()
+    if gelu:
+        ref = orc.gelu_erf(ref)
+    if resid:
+        ref = ref + r.double()
+    y = mt.ops.linear_fp8(xq, wq, sx * sw, bias=b.cuda(), residual=None if r is None else r.cuda().bfloat16(), gelu=gelu)
+    err = (y.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2 ** -8, f"fp8 GEMM on quantised operands: {err:.2e}"
+    # against the unquantised product the error is the e4m3 quantisation error (3 mantissa bits per operand)
+    full = x.double() @ w.double().t() + b.double()
+    if not gelu and not resid:
+        assert float((y.double().cpu() - full).norm() / full.norm()) < 0.08
