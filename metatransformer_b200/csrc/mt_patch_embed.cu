@@ -12,6 +12,7 @@
 // walk K fastest so stores are fully coalesced and loads are whole 32/64-byte segments.
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
+#include <stdlib.h>
 
 namespace mt {
 
@@ -84,80 +85,76 @@ im2row_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const
   }
 }
 
-// Vector path without per-element index arithmetic (ncu, round 2: the kernel above was issue-bound at 73 % issue-slot
-// utilisation / 57 % of DRAM peak — six integer divisions per 16-byte store).  A 256-thread block is laid out as
-// rpb token rows x tpr K-segments (tpr = min(K/8, 256)); a thread's K offset (which 8-pixel segment of which (c, dt, dh)
-// row) does not depend on the token and is decoded once, the token coordinates are decoded once per run and then advanced
-// incrementally; four tokens are in flight per thread (eight 16-byte loads) before the first store.
-constexpr int kRun = 64;         // tokens per block iteration and token row of the block
-constexpr int kMaxSeg = 4;       // 8-element K segments per thread (K <= 8192)
-
-struct TokenPos { int b, tp, hp, wp; };
-MT_DEVINL void token_advance(TokenPos& t, int step, const Im2RowParams& p) {
-  t.wp += step;
-  while (t.wp >= p.Wp) {
-    t.wp -= p.Wp;
-    if (++t.hp == p.Hp) { t.hp = 0; if (++t.tp == p.Tp) { t.tp = 0; ++t.b; } }
-  }
-}
+// Vector path with the index arithmetic tabled per block (ncu, round 2: the kernel above is issue-bound — 73 % issue-slot
+// utilisation at 57 % of DRAM peak, six integer divisions per 16-byte store).  One element per thread and a huge grid,
+// like above (two "run per thread" variants with fewer, longer-lived threads measured 1.6-4x slower), but a 256-thread block
+// = rpb token rows x tpr K-segments whose K offsets and token base offsets are decoded once per block into shared memory.
+constexpr int kTabTok = 8;   // tokens per thread row and block iteration (independent loads in flight per thread)
 
 template <typename TIn>
 __global__ void __launch_bounds__(256)
-im2row_run_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const Im2RowParams p, int tpr, int rpb) {
+im2row_tab_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const Im2RowParams p, int tpr, int rpb) {
+  __shared__ long long koff_s[256];
+  __shared__ long long base_s[256];
   const int k8_per_row = p.K >> 3;
-  const int rl = int(threadIdx.x) / tpr;        // token row of this thread inside the block
-  const int kt0 = int(threadIdx.x) - rl * tpr;  // its first K segment
-  if (rl >= rpb) return;
-  long long koff[kMaxSeg];
-#pragma unroll
-  for (int i = 0; i < kMaxSeg; ++i) {
-    int kk = (kt0 + tpr * i) << 3;
-    const int dw0 = kk % p.kw; kk /= p.kw;
-    const int dh = kk % p.kh; kk /= p.kh;
-    const int dt = kk % p.kt;
-    const int c = kk / p.kt;
-    koff[i] = ((long long)(c * p.T + dt) * p.H + dh) * p.W + dw0;
-  }
+  const int tid = int(threadIdx.x);
+  const int rl = tid / tpr;
+  const int kt = tid - rl * tpr;
+  const int segs = (k8_per_row + tpr - 1) / tpr;          // K segments per thread (1 unless K > 2048)
   const long long plane = (long long)p.H * p.W;
-  const int nseg = (k8_per_row + tpr - 1) / tpr;
-  for (long long m0 = (long long)blockIdx.x * kRun; m0 < p.M; m0 += (long long)gridDim.x * kRun) {
-    long long r = m0 + rl;
-    TokenPos tk;
-    tk.wp = int(r % p.Wp); r /= p.Wp;
-    tk.hp = int(r % p.Hp); r /= p.Hp;
-    tk.tp = int(r % p.Tp);
-    tk.b = int(r / p.Tp);
-    const long long m_end = min(m0 + (long long)kRun, p.M);
-    for (long long m = m0 + rl; m < m_end; m += 4LL * rpb) {
-      long long base[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ok[u] = (m + (long long)u * rpb) < m_end;
-        base[u] = ((long long)tk.b * p.C * p.T + (long long)tk.tp * p.st) * plane + (long long)(tk.hp * p.sh) * p.W + tk.wp * p.sw;
-        token_advance(tk, rpb, p);
+  const int tok_per_iter = rpb * kTabTok;                 // <= 256
+  auto decode_k = [&](int sg) {
+    if (tid < tpr) {
+      int kk = (tid + tpr * sg) << 3;
+      const int dw0 = kk % p.kw; kk /= p.kw;
+      const int dh = kk % p.kh; kk /= p.kh;
+      const int dt = kk % p.kt;
+      const int c = kk / p.kt;
+      koff_s[tid] = ((long long)(c * p.T + dt) * p.H + dh) * p.W + dw0;
+    }
+  };
+  if (segs == 1) decode_k(0);
+  for (long long m0 = (long long)blockIdx.x * tok_per_iter; m0 < p.M; m0 += (long long)gridDim.x * tok_per_iter) {
+    __syncthreads();
+    if (tid < tok_per_iter) {
+      long long r = m0 + tid;
+      const int wp = int(r % p.Wp); r /= p.Wp;
+      const int hp = int(r % p.Hp); r /= p.Hp;
+      const int tp = int(r % p.Tp);
+      const long long b = r / p.Tp;
+      base_s[tid] = (b * p.C * p.T + (long long)tp * p.st) * plane + (long long)(hp * p.sh) * p.W + wp * p.sw;
+    }
+    for (int sg = 0; sg < segs; ++sg) {
+      if (segs > 1) {
+        __syncthreads();
+        decode_k(sg);
       }
+      __syncthreads();
+      const int k8 = kt + tpr * sg;
+      if (rl < rpb && k8 < k8_per_row) {
+        const long long ko = koff_s[kt];
+        uint4 o[kTabTok];
 #pragma unroll
-      for (int i = 0; i < kMaxSeg; ++i) {
-        const int k8 = kt0 + tpr * i;
-        if (i >= nseg || k8 >= k8_per_row) continue;
-        uint4 o[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (!ok[u]) continue;
-          if constexpr (sizeof(TIn) == 4) {
-            const float4* src = reinterpret_cast<const float4*>(x + base[u] + koff[i]);
-            const float4 a = __ldg(src);
-            const float4 c4 = __ldg(src + 1);
-            o[u].x = pack_bf16x2(a.x, a.y); o[u].y = pack_bf16x2(a.z, a.w);
-            o[u].z = pack_bf16x2(c4.x, c4.y); o[u].w = pack_bf16x2(c4.z, c4.w);
-          } else {
-            o[u] = __ldg(reinterpret_cast<const uint4*>(x + base[u] + koff[i]));
+        for (int u = 0; u < kTabTok; ++u) {
+          const int tl = rl + rpb * u;                     // token of this thread inside the iteration
+          if (m0 + tl < p.M) {
+            const long long off = base_s[tl] + ko;
+            if constexpr (sizeof(TIn) == 4) {
+              const float4* src = reinterpret_cast<const float4*>(x + off);
+              const float4 a = __ldg(src);
+              const float4 c4 = __ldg(src + 1);
+              o[u].x = pack_bf16x2(a.x, a.y); o[u].y = pack_bf16x2(a.z, a.w);
+              o[u].z = pack_bf16x2(c4.x, c4.y); o[u].w = pack_bf16x2(c4.z, c4.w);
+            } else {
+              o[u] = __ldg(reinterpret_cast<const uint4*>(x + off));
+            }
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (ok[u]) *reinterpret_cast<uint4*>(rows + size_t(m + (long long)u * rpb) * p.K + (k8 << 3)) = o[u];
+        for (int u = 0; u < kTabTok; ++u) {
+          const int tl = rl + rpb * u;
+          if (m0 + tl < p.M) *reinterpret_cast<uint4*>(rows + size_t(m0 + tl) * p.K + (k8 << 3)) = o[u];
+        }
       }
     }
   }
@@ -179,13 +176,18 @@ static int launch_im2row(const void* x, void* rows, const Im2RowParams& p, cudaS
                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (8 % seg_align == 0);
   const TIn* xp = reinterpret_cast<const TIn*>(x);
   __nv_bfloat16* rp = reinterpret_cast<__nv_bfloat16*>(rows);
-  if (vec && (p.K >> 3) <= 256 * kMaxSeg) {
+  static int use_tab = -1;    // MT_B200_IM2ROW_TAB=0 selects the plain vector kernel (A/B runs)
+  if (use_tab < 0) {
+    const char* e = getenv("MT_B200_IM2ROW_TAB");
+    use_tab = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (vec && use_tab) {
     const int k8 = p.K >> 3;
     const int tpr = k8 < 256 ? k8 : 256;
     const int rpb = 256 / tpr;
-    long long runs = (p.M + kRun - 1) / kRun;
-    long long rblocks = runs < (long long)sms * 16 ? runs : (long long)sms * 16;
-    im2row_run_kernel<TIn><<<unsigned(rblocks), 256, 0, s>>>(xp, rp, p, tpr, rpb);
+    long long nb = (p.M + rpb * kTabTok - 1) / (rpb * kTabTok);
+    if (nb > (long long)sms * 32) nb = (long long)sms * 32;
+    im2row_tab_kernel<TIn><<<unsigned(nb), 256, 0, s>>>(xp, rp, p, tpr, rpb);
   } else if (vec) im2row_kernel<TIn, true><<<unsigned(blocks), 256, 0, s>>>(xp, rp, p);
   else im2row_kernel<TIn, false><<<unsigned(blocks), 256, 0, s>>>(xp, rp, p);
   MT_CHECK_CUDA(cudaGetLastError());
