@@ -36,10 +36,10 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.randn(5, 16, generator=g)
     model(x).square().mean().backward()
-    local = [p.grad.clone() for p in model.parameters() if p.grad is not None]
+    local = [p.grad.flatten().tolist() for p in model.parameters() if p.grad is not None]
     n = allreduce_gradients(model.parameters(), world, bucket_bytes=1024)
-    out = [p.grad.clone() for p in model.parameters() if p.grad is not None]
-    q.put((rank, n, local, out))
+    out = [p.grad.flatten().tolist() for p in model.parameters() if p.grad is not None]
+    q.put((rank, n, local, out))      # plain lists: tensors sent through a Queue race with the sender's exit
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,6 +61,7 @@ def test_gradient_allreduce_world2_gloo():
     assert n0 == n1 and n0 >= 2                    # several 1 KB buckets
     assert len(o0) == 3                            # weight0, bias0, bias1 (frozen weight has no grad)
     for a, b, x, y in zip(l0, l1, o0, o1):
+        a, b, x, y = (torch.tensor(t) for t in (a, b, x, y))
         assert torch.allclose(x, (a + b) / 2, atol=1e-6) and torch.allclose(x, y)
 
 
