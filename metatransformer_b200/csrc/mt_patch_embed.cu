@@ -87,7 +87,7 @@ im2row_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ rows, const
 
 // Vector path with the index arithmetic tabled per block (ncu, round 2: the kernel above is issue-bound — 73 % issue-slot
 // utilisation at 57 % of DRAM peak, six integer divisions per 16-byte store).  One element per thread and a huge grid,
-// like above (two "run per thread" variants with fewer, longer-lived threads measured 1.6-4x slower), but a 256-thread block
+// like above (two "run per thread" variants with fewer, longer-lived threads measured 1.6-4x slower on C1), but a 256-thread block
 // = rpb token rows x tpr K-segments whose K offsets and token base offsets are decoded once per block into shared memory.
 constexpr int kTabTok = 8;   // tokens per thread row and block iteration (independent loads in flight per thread)
 
@@ -176,12 +176,15 @@ static int launch_im2row(const void* x, void* rows, const Im2RowParams& p, cudaS
                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (8 % seg_align == 0);
   const TIn* xp = reinterpret_cast<const TIn*>(x);
   __nv_bfloat16* rp = reinterpret_cast<__nv_bfloat16*>(rows);
-  static int use_tab = -1;    // MT_B200_IM2ROW_TAB=0 selects the plain vector kernel (A/B runs)
-  if (use_tab < 0) {
+  // The tabled kernel wins on long patch rows (C5 tubelets, K = 1536: 284 vs 364 us for the whole tokenizer call, same box)
+  // and loses on short ones (C1 image patches, K = 768: 235 vs 133 us): default by K, MT_B200_IM2ROW_TAB=0|1 forces one.
+  static int use_tab = -2;
+  if (use_tab == -2) {
     const char* e = getenv("MT_B200_IM2ROW_TAB");
-    use_tab = (e && e[0] == '0') ? 0 : 1;
+    use_tab = (e && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
   }
-  if (vec && use_tab) {
+  const bool tab = use_tab >= 0 ? (use_tab == 1) : (p.K >= 1024);
+  if (vec && tab) {
     const int k8 = p.K >> 3;
     const int tpr = k8 < 256 ? k8 : 256;
     const int rpb = 256 / tpr;
