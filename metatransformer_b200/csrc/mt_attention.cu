@@ -76,6 +76,9 @@ struct AttnParams {
   uint32_t seed_lo, seed_hi;
 };
 
+// kDrop: attention dropout compiled in (the keep test sits in the innermost loop: a run-time flag there costs a branch per
+// score pair — 13 % of the softmax warps' stall samples were branch resolution in the round-2 capture)
+template <bool kDrop>
 __global__ void __launch_bounds__(kAtThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
@@ -402,7 +405,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 float e0 = ex2_approx(a0);
                 float e1 = ex2_approx(a1);
                 l2 = add_f32x2(l2, pack_f32x2(e0, e1));
-                if (p.drop_thresh != 0u) {
+                if constexpr (kDrop) {
                   const uint32_t kidx = drop_row + uint32_t(j * kAtBN + 16 * qi + 8 * g + 2 * i);
                   if (!attn_keep(bh_seed, kidx, p.drop_thresh)) e0 = 0.f;
                   if (!attn_keep(bh_seed, kidx + 1u, p.drop_thresh)) e1 = 0.f;
@@ -449,7 +452,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 float e0 = ex2_approx(a0);
                 float e1 = ex2_approx(a1);
                 l2 = add_f32x2(l2, pack_f32x2(e0, e1));
-                if (p.drop_thresh != 0u) {
+                if constexpr (kDrop) {
                   const uint32_t kidx = drop_row + uint32_t(j * kAtBN + 16 * qi + 8 * g + 2 * i);
                   if (!attn_keep(bh_seed, kidx, p.drop_thresh)) e0 = 0.f;
                   if (!attn_keep(bh_seed, kidx + 1u, p.drop_thresh)) e1 = 0.f;
@@ -588,13 +591,19 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
     int dev = 0;
     MT_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
-      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
-  MT_CHECK_CUDA(launch_pdl(attention_fwd_kernel, dim3(unsigned(grid)), dim3(kAtThreads), size_t(kAtSmemBytes),
-                           reinterpret_cast<cudaStream_t>(stream), 1u, tm_q, tm_kv, tm_out, p));
+  if (p.drop_thresh != 0u)
+    MT_CHECK_CUDA(launch_pdl(attention_fwd_kernel<true>, dim3(unsigned(grid)), dim3(kAtThreads), size_t(kAtSmemBytes),
+                             reinterpret_cast<cudaStream_t>(stream), 1u, tm_q, tm_kv, tm_out, p));
+  else
+    MT_CHECK_CUDA(launch_pdl(attention_fwd_kernel<false>, dim3(unsigned(grid)), dim3(kAtThreads), size_t(kAtSmemBytes),
+                             reinterpret_cast<cudaStream_t>(stream), 1u, tm_q, tm_kv, tm_out, p));
   return MT_OK;
 }
 

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_store_kernel(const float* __r
   }
 }
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kAbThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                      const __grid_constant__ CUtensorMap tm_dq, const AttnBwdParams p) {
@@ -431,7 +432,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
           float p1 = ex2f(fmaf(__uint_as_float(s[c0 + 1]), c, -l2.y));
           if (!key_ok) { p0 = 0.f; p1 = 0.f; }
           float m0 = 1.f, m1 = 1.f;
-          if (p.drop_thresh != 0u) {
+          if constexpr (kDrop) {
             const uint32_t qidx = uint32_t(cur.i * 128 + 64 * hf + 32 * sub + c0) * uint32_t(p.N) + key_idx;
             m0 = attn_keep(bh_seed, qidx, p.drop_thresh) ? p.drop_scale : 0.f;
             m1 = attn_keep(bh_seed, qidx + uint32_t(p.N), p.drop_thresh) ? p.drop_scale : 0.f;
@@ -577,7 +578,8 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     int dev = 0;
     MT_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
@@ -590,7 +592,8 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     int rc2 = encode_tmap(&tm_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc2) return rc2;
   }
-  attention_bwd_kernel<<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, tm_dq, p);
+  if (p.drop_thresh != 0u) attention_bwd_kernel<true><<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, tm_dq, p);
+  else attention_bwd_kernel<false><<<unsigned(grid), kAbThreads, kAbSmemBytes, s>>>(tm_qkv, tm_do, tm_dq, p);
   MT_CHECK_CUDA(cudaGetLastError());
   if (!p.resident) {
     const long long rows = (long long)B * N;
