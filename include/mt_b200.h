@@ -174,6 +174,14 @@ int mt_attention_bwd_ex(const void* qkv, const void* out, const void* dout, cons
                         unsigned long long seed, void* stream);
 int mt_attention_dropout_mask(void* mask, int B, int N, int H, float drop_p, unsigned long long seed, void* stream);
 
+/* Debugging hook (tools/attn_trace.py): in builds compiled with -DMT_ATTN_TRACE=1 the following attention forward
+ * launches log (clock64 << 8 | event id) per warp of CTAs 0 and 1 into buf (device memory, 2 x 12 x 1024 int64);
+ * nullptr switches it off.  Returns 1 (and does nothing) in the shipped build, which has no trace points. */
+int mt_attention_set_trace(void* buf);
+/* Same for the GEMM kernel (tools/gemm_trace.py, -DMT_GEMM_TRACE=1): cycles every warp of CTAs 0-3 spends in its barrier
+ * waits, 4 x 20 x 8 int64.  Returns 1 in the shipped build. */
+int mt_gemm_set_trace(void* buf);
+
 /* ---- T1/T2/T3: patch / spectrogram / tubelet embedding -----------------------------------------------------
  * Non-overlapping or strided Conv{2,3}d as im2row + GEMM.
  * mt_im2row: x [B, C, T, H, W] (x_dtype fp32 or bf16; T = kt = 1 for 2-D) -> rows bf16 [B*Tp*Hp*Wp, C*kt*kh*kw]

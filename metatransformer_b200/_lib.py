@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "mt_dropout", "mt_pad_cols", "mt_cast", "mt_encoder_create", "mt_encoder_destroy", "mt_encoder_workspace_bytes",
     "mt_encoder_forward", "mt_encoder_forward_ex", "mt_encoder_launches_per_forward",
     "mt_row_stats_split", "mt_ln_stats_finalize", "mt_center_split", "mt_embed_sum", "mt_split_f32", "mt_merge_f32", "mt_timeline_begin", "mt_timeline_end", "mt_allreduce", "mt_attention_fwd_ex", "mt_attention_bwd_ex",
-    "mt_attention_dropout_mask", "mt_quantize_fp8", "mt_gemm_fp8", "mt_split_tf32", "mt_layernorm_f32_split", "mt_gemm_f32x3", "mt_attention_f32",
+    "mt_attention_dropout_mask", "mt_attention_set_trace", "mt_gemm_set_trace", "mt_quantize_fp8", "mt_gemm_fp8", "mt_split_tf32", "mt_layernorm_f32_split", "mt_gemm_f32x3", "mt_attention_f32",
 )
 
 
@@ -149,6 +149,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.mt_attention_bwd_ex.restype = c_int
     lib.mt_attention_bwd_ex.argtypes = [c_void_p] * 6 + [c_size_t, c_int, c_int, c_int, c_int, c_float, c_float, c_ulonglong,
                                                          c_void_p]
+    lib.mt_gemm_set_trace.restype = c_int
+    lib.mt_gemm_set_trace.argtypes = [c_void_p]
+    lib.mt_attention_set_trace.restype = c_int
+    lib.mt_attention_set_trace.argtypes = [c_void_p]
     lib.mt_attention_dropout_mask.restype = c_int
     lib.mt_attention_dropout_mask.argtypes = [c_void_p, c_int, c_int, c_int, c_float, c_ulonglong, c_void_p]
     lib.mt_quantize_fp8.restype = c_int

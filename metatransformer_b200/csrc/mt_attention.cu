@@ -3,30 +3,43 @@
 //   (PointCloud/openpoints/models/layers/attention.py:31-35; Image/.../base/vit.py:108-112 is the same math).
 // The reference materialises the B*H*N*N score matrix; here S and P never leave the SM.
 //
-// Blackwell design (sm_100a only), head_dim = 64, no mask, no dropout:
+// Blackwell design (sm_100a only), head_dim = 64, no mask, optional attention dropout:
 //   * q, k, v are read straight out of the packed (B, N, 3, H, 64) qkv buffer through one 4-D TMA descriptor
 //     (no permute / contiguous copies), output is written straight into (B, N, H*64) through a 4-D TMA store;
 //   * persistent CTAs, TWO per SM (108 KB of shared memory, 256 TMEM columns, 96 registers per softmax thread each):
-//     the kernel is bound by the softmax warps' instruction latency and by MUFU (one ex2 per score: 16 / clk / SM is
-//     the same 47 us floor as the HBM traffic at C2), so what counts is how many independent softmax instruction
-//     streams an SM scheduler can pick from — 4 warps per scheduler here against 2 in the one-CTA-per-SM version;
-//   * a work item is (batch, head, 256 query rows) = two 128-row query tiles that ping-pong: while the softmax warps
-//     of tile 0 work on S0, the tensor core computes S1 / P1·V, and vice versa; warps whose 32 query rows all lie
-//     beyond N only keep the barrier protocol going;
-//   * S = Q·K^T and O += P·V are tcgen05.mma (bf16 in, fp32 accumulate) with S and O living in TMEM
-//     (S0,S1: 2 x 64 columns, O0,O1: 2 x 64 columns); V is consumed as an MN-major operand so no transpose;
-//   * online softmax in fp32 registers, one query row per thread (tcgen05.ld 32x32b), exp2 with the
-//     scale*log2(e) factor folded in; P goes back as bf16 through 128B-swizzled smem; the last key tile is
-//     processed in 16-key quarters (N = 196: 4 valid keys -> one quarter);
-//   * K/V tiles (64 keys) stream through 3- / 2-stage TMA rings shared by both query tiles.
+//     the kernel is bound by MUFU (one ex2 per score: 16 / clk / SM is the same 47 us floor as the HBM traffic at C2)
+//     and by the softmax warps' instruction latency, so what counts is how many independent softmax instruction streams
+//     an SM scheduler can pick from (4 warps per scheduler) and that none of them ever waits for the tensor core;
+//   * a work item is (batch, head, 256 query rows) = two 128-row query tiles that ping-pong; warps whose 32 query rows
+//     all lie beyond N only keep the barrier protocol going;
+//   * S = Q·K^T and O += P·V are tcgen05.mma (bf16 in, fp32 accumulate) with S and O living in TMEM.  The unit of the
+//     softmax pipeline is a HALF key tile of 32 keys: S_t has two 32-column halves (TMEM columns 64 t + 32 h) that are
+//     computed by separate N = 32 MMAs with their own barriers.  A softmax thread (one query row) pulls its 32 scores
+//     with ONE tcgen05.ld, releases the half immediately (the issuer then computes the scores two halves ahead into
+//     it while the warp is busy with the exponentials) and does max / exp2 / row sum / bf16 pack from registers —
+//     one pass, nothing is read from TMEM twice;
+//   * online softmax in fp32 registers with lazy rescaling, exp2 with the scale*log2(e) factor folded in; P goes back
+//     as bf16 through the 128B-swizzled P_t tile (half h = 64 bytes of every row), P_t-half·V is issued per half;
+//   * the exponentials are a pure MUFU burst (32 ex2 per thread and half) and the MUFU pipe arbitrates per instruction,
+//     so the four softmax warps of a scheduler drift into a convoy: all burst together at a quarter of the rate each,
+//     then all do their barrier / tcgen05.ld / max work together while the MUFU pipe idles (39 % MUFU-active in the
+//     round-2 capture, with per-half times that were the SUM of the phases).  The two warps of a CTA that share a
+//     scheduler (same lane quarter of tile 0 and tile 1) therefore take turns for the burst through a pair of named
+//     barriers: one computes exponentials while the other waits for / loads / reduces its next scores;
+//   * K/V tiles (64 keys = two halves) stream through 3- / 2-stage TMA rings shared by both query tiles; the last half
+//     of a row of keys runs at N = 16 when it holds at most 16 valid keys (N = 196: 4 keys).
 //
 // Warps (384 threads): 0-3 softmax tile 0, 4-7 softmax tile 1 (warp%4 = TMEM lane quarter), 8 = TMA loader,
 // 9 = S=QK^T issuer + TMEM allocator, 10 = O+=PV issuer, 11 idle (completes the third warpgroup for setmaxnreg).
 // a timed-out barrier wait traps without the device printf: the call sequence costs the 40-register role warps spills
 #define MT_WAIT_QUIET 1
-#ifndef MT_ATTN_ONE_PASS
-#define MT_ATTN_ONE_PASS 0   // 1: whole score row in registers (does not fit 96 registers: kept for A/B builds only)
+#ifndef MT_ATTN_PINGPONG
+#define MT_ATTN_PINGPONG 0   // 1: A/B builds with MUFU turn-taking between the two query tiles (measured 2-9 % slower)
 #endif
+#ifndef MT_ATTN_TRACE
+#define MT_ATTN_TRACE 0   // 1: debugging build that logs (clock64 << 8 | event id) per warp for the first two CTAs
+#endif
+#include <type_traits>
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 
@@ -34,7 +47,8 @@ namespace mt {
 
 constexpr int kAtQT = 2;                    // query tiles per CTA
 constexpr int kAtBM = 128;                  // query rows per tile
-constexpr int kAtBN = 64;                   // keys per KV tile
+constexpr int kAtBN = 64;                   // keys per KV tile (one TMA box)
+constexpr int kAtHN = 32;                   // keys per half tile (one softmax step)
 constexpr int kAtD = 64;                    // head dim
 constexpr int kAtKStages = 3;
 constexpr int kAtVStages = 2;
@@ -46,12 +60,13 @@ constexpr int kAtSmemP = kAtSmemQ + kAtQT * kAtQBytes;
 constexpr int kAtSmemK = kAtSmemP + kAtQT * kAtQBytes;
 constexpr int kAtSmemV = kAtSmemK + kAtKStages * kAtKVBytes;
 constexpr int kAtSmemBar = kAtSmemV + kAtVStages * kAtKVBytes;
-// barriers: q_full[2] q_empty[2] k_full[3] k_empty[3] v_full[2] v_empty[2] s_full[2] s_empty[2] p_full[2] o_done[2]
-constexpr int kAtNumBars = 2 * kAtQT + 2 * kAtKStages + 2 * kAtVStages + 4 * kAtQT;
+// barriers: q_full[2] q_empty[2] k_full[3] k_empty[3] v_full[2] v_empty[2], then per (tile, half):
+// s_full[4] s_empty[4] p_full[4] pv_done[4]
+constexpr int kAtNumBars = 2 * kAtQT + 2 * kAtKStages + 2 * kAtVStages + 8 * kAtQT;
 constexpr int kAtSmemTmemPtr = kAtSmemBar + kAtNumBars * 8;
-constexpr int kAtSmemBytes = kAtSmemTmemPtr + 16 + 1024;   // 107.7 KB: two CTAs per SM
+constexpr int kAtSmemBytes = kAtSmemTmemPtr + 16 + 1024;   // 107.8 KB: two CTAs per SM
 constexpr int kAtTmemCols = 256;   // two CTAs per SM share the 512 columns
-constexpr int kAtTmemS = 0;        // S_t at columns 64*t
+constexpr int kAtTmemS = 0;        // S_t half h at columns 64*t + 32*h
 constexpr int kAtTmemO = 128;      // O_t at columns 128 + 64*t
 static_assert(2 * (kAtSmemBytes + 1024) <= 233472, "two attention CTAs must fit one SM's shared memory");
 
@@ -65,10 +80,12 @@ struct AttnParams {
   int B, N, H;
   int num_qp;        // ceil(N / 256)
   int num_kv;        // ceil(N / 64)
+  int num_half;      // ceil(N / 32)
   int num_items;     // B * H * num_qp
   float scale_log2;  // scale * log2(e)
   float* lse2;       // optional [B, H, N]: log2-sum-exp of the scaled scores (m*c + log2 l), saved for the backward
   unsigned long long* tl;   // optional timeline slot (mt_timeline_begin)
+  long long* trace;         // MT_ATTN_TRACE builds only: per-warp event log (tools/attn_trace.py), else unused
   // attention dropout (training, Graph fork): P is multiplied by keep(q, k) before P.V and O by 1 / (1 - p); the row sum
   // l stays the sum of the undropped probabilities (softmax first, dropout second: attention.py:32-33)
   uint32_t drop_thresh;     // p * 2^32, 0 = no dropout
@@ -96,10 +113,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   auto v_full = [&](int s) { return bar0 + 8u * (4 + 2 * kAtKStages + s); };
   auto v_empty = [&](int s) { return bar0 + 8u * (4 + 2 * kAtKStages + kAtVStages + s); };
   constexpr int kB2 = 4 + 2 * kAtKStages + 2 * kAtVStages;
-  auto s_full = [&](int t) { return bar0 + 8u * (kB2 + t); };
-  auto s_empty = [&](int t) { return bar0 + 8u * (kB2 + 2 + t); };
-  auto p_full = [&](int t) { return bar0 + 8u * (kB2 + 4 + t); };
-  auto o_done = [&](int t) { return bar0 + 8u * (kB2 + 6 + t); };
+  // th = 2 * tile + half
+  auto s_full = [&](int th) { return bar0 + 8u * (kB2 + th); };
+  auto s_empty = [&](int th) { return bar0 + 8u * (kB2 + 4 + th); };
+  auto p_full = [&](int th) { return bar0 + 8u * (kB2 + 8 + th); };
+  auto pv_done = [&](int th) { return bar0 + 8u * (kB2 + 12 + th); };
   auto q_smem = [&](int t) { return smem_base + uint32_t(kAtSmemQ + t * kAtQBytes); };
   const uint32_t tmem_ptr_addr = smem_base + kAtSmemTmemPtr;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kAtSmemTmemPtr);
@@ -111,10 +129,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     for (int t = 0; t < kAtQT; ++t) {
       mbar_init(q_full(t), 1);
       mbar_init(q_empty(t), 1);
-      mbar_init(s_full(t), 1);
-      mbar_init(s_empty(t), 4);  // one arrive per softmax warp
-      mbar_init(p_full(t), 4);
-      mbar_init(o_done(t), 1);
+    }
+    for (int th = 0; th < 2 * kAtQT; ++th) {
+      mbar_init(s_full(th), 1);
+      mbar_init(s_empty(th), 4);  // one arrive per softmax warp
+      mbar_init(p_full(th), 4);
+      mbar_init(pv_done(th), 1);
     }
     for (int s = 0; s < kAtKStages; ++s) {
       mbar_init(k_full(s), 1);
@@ -137,9 +157,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   timeline_start(p.tl);
 
   const int H = p.H;
+  const int G = p.num_half;
+#if MT_ATTN_TRACE == 1
+  constexpr int kTrMax = 1024;
+  int tr_n = 0;
+#define TR(id)                                                                                              \
+  do {                                                                                                      \
+    if (p.trace != nullptr && blockIdx.x < 2 && lane == 0 && tr_n < kTrMax)                                 \
+      p.trace[(size_t(blockIdx.x) * 12 + warp) * kTrMax + tr_n++] = (clock64() << 8) | (long long)(id);     \
+  } while (0)
+#else
+#define TR(id) do { } while (0)
+#endif
+#if MT_ATTN_TRACE == 2
+  // wait-time accounting: cycles each warp spends inside its barrier waits, by kind (slots 0..3), + kernel cycles
+  long long wt0 = 0, wt1 = 0, wt2 = 0, wt3 = 0;
+  const long long wt_begin = clock64();
+#define WT(slot, stmt)                                   \
+  do {                                                   \
+    const long long a_ = clock64();                      \
+    stmt;                                                \
+    wt##slot += clock64() - a_;                          \
+  } while (0)
+#else
+#define WT(slot, stmt) do { stmt; } while (0)
+#endif
 
   // register re-distribution between warpgroups (compiled for 80/thread: two CTAs per SM): the softmax warpgroups hold
-  // a whole 64-column score row per thread, the loader / MMA warpgroup needs almost nothing
+  // a 32-column score row per thread plus the exp / pack temporaries, the loader / MMA warpgroup needs almost nothing
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
@@ -155,16 +200,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int bh = item / p.num_qp;
         const int h = bh % H, b = bh / H;
         for (int t = 0; t < kAtQT; ++t) {
-          mbar_wait(q_empty(t), (it & 1u) ^ 1u);
+          WT(0, mbar_wait(q_empty(t), (it & 1u) ^ 1u));
           mbar_arrive_expect_tx(q_full(t), kAtQBytes);
+          TR(40 + t);
           tma_load_4d(q_smem(t), &tm_q, q_full(t), 0, h, qp * 256 + t * 128, b, kEvictFirst);
         }
         for (int j = 0; j < p.num_kv; ++j) {
-          mbar_wait(k_empty(kst), kph ^ 1u);
+          WT(1, mbar_wait(k_empty(kst), kph ^ 1u));
+          TR(42);
           mbar_arrive_expect_tx(k_full(kst), kAtKVBytes);
           tma_load_4d(smem_base + kAtSmemK + kst * kAtKVBytes, &tm_kv, k_full(kst), 0, H + h, j * kAtBN, b, kv_hint);
           if (++kst == kAtKStages) { kst = 0; kph ^= 1u; }
-          mbar_wait(v_empty(vst), vph ^ 1u);
+          WT(2, mbar_wait(v_empty(vst), vph ^ 1u));
+          TR(43);
           mbar_arrive_expect_tx(v_full(vst), kAtKVBytes);
           tma_load_4d(smem_base + kAtSmemV + vst * kAtKVBytes, &tm_kv, v_full(vst), 0, 2 * H + h, j * kAtBN, b,
                       kv_hint);
@@ -176,32 +224,43 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     // =============================== S = Q K^T issuer ============================
     // Two single-thread MMA issuers (this warp and warp 10) instead of one: the tcgen05.mma of a work item issued from one
     // thread (descriptor arithmetic + barrier polls are a serial dependency chain) were the critical path.
-    // This thread runs ahead on its own, throttled only by s_empty (the softmax warps pulled S_t into registers).
+    // This thread runs ahead on its own, throttled only by s_empty (the softmax warps pulled a half of S_t into registers:
+    // the half is then free for the scores two halves further on).
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kAtBM, kAtBN, 0, 0);   // both operands K-major
       int kst = 0; uint32_t kph = 0;
-      uint32_t n_s0 = 0, n_s1 = 0;   // S_t tiles issued so far
+      uint32_t n_h0 = 0, n_h1 = 0;   // uses of half 0 / half 1 so far (the same for both query tiles)
       uint32_t it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        // One MMA group per 64-key tile and query tile (N = the valid keys rounded up to 16): every tcgen05.mma with
+        // both operands in shared memory occupies the tensor pipe for at least ~60 cycles however small N is
+        // (tools/bench_umma.cu), so the scores of both halves are produced by the same four instructions and only their
+        // hand-over to the softmax warps is per half.
         for (int j = 0; j < p.num_kv; ++j) {
-          mbar_wait(k_full(kst), kph);
+          WT(0, mbar_wait(k_full(kst), kph));
+          TR(20);
           const uint64_t bdesc = make_smem_desc_sw128(smem_base + kAtSmemK + kst * kAtKVBytes);
+          const int valid = min(kAtBN, p.N - j * kAtBN);
+          const bool two = valid > kAtHN;                         // the tile has a second half
+          const uint32_t idesc = make_idesc_bf16(kAtBM, (valid + 15) & ~15, 0, 0);   // both operands K-major
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
-            if (j == 0) mbar_wait(q_full(t), it & 1u);
-            uint32_t& n_s = (t == 0) ? n_s0 : n_s1;
-            mbar_wait(s_empty(t), (n_s & 1u) ^ 1u);
-            ++n_s;
+            if (j == 0) { WT(1, mbar_wait(q_full(t), it & 1u)); TR(21); }
+            WT(2, mbar_wait(s_empty(2 * t + 0), (n_h0 & 1u) ^ 1u));
+            if (two) WT(3, mbar_wait(s_empty(2 * t + 1), (n_h1 & 1u) ^ 1u));
+            TR(22 + t);
             tc_fence_after();
             const uint64_t adesc = make_smem_desc_sw128(q_smem(t));
-            const uint32_t d_tmem = tmem_base + kAtTmemS + t * kAtBN;
-            umma_f16_ss<1>(d_tmem, adesc, bdesc, idesc_s, 0u);
-            umma_f16_ss<1>(d_tmem, adesc + 2u, bdesc + 2u, idesc_s, 1u);
-            umma_f16_ss<1>(d_tmem, adesc + 4u, bdesc + 4u, idesc_s, 1u);
-            umma_f16_ss<1>(d_tmem, adesc + 6u, bdesc + 6u, idesc_s, 1u);
-            umma_commit(s_full(t));
+            const uint32_t d_tmem = tmem_base + uint32_t(kAtTmemS + t * kAtBN);
+            umma_f16_ss<1>(d_tmem, adesc, bdesc, idesc, 0u);
+            umma_f16_ss<1>(d_tmem, adesc + 2u, bdesc + 2u, idesc, 1u);
+            umma_f16_ss<1>(d_tmem, adesc + 4u, bdesc + 4u, idesc, 1u);
+            umma_f16_ss<1>(d_tmem, adesc + 6u, bdesc + 6u, idesc, 1u);
+            umma_commit(s_full(2 * t + 0));
+            if (two) umma_commit(s_full(2 * t + 1));
             if (j + 1 == p.num_kv) umma_commit(q_empty(t));   // last use of Q_t for this item
           }
+          ++n_h0;
+          if (two) ++n_h1;
           umma_commit(k_empty(kst));
           if (++kst == kAtKStages) { kst = 0; kph ^= 1u; }
         }
@@ -212,34 +271,36 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc_o = make_idesc_bf16(kAtBM, kAtD, 0, 1);    // V is consumed MN-major
       int vst = 0; uint32_t vph = 0;
-      uint32_t n_p0 = 0, n_p1 = 0;   // P_t tiles consumed so far
+      uint32_t n_h0 = 0, n_h1 = 0;   // P halves consumed so far
+      uint64_t bdesc0 = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        for (int j = 0; j < p.num_kv; ++j) {
-          const int valid = min(kAtBN, p.N - j * kAtBN);
-          const int ksteps = (valid + 15) >> 4;   // 16-key steps covering the valid keys
-          mbar_wait(v_full(vst), vph);
-          const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + kAtSmemV + vst * kAtKVBytes);
+        for (int g = 0; g < G; ++g) {
+          const int hf = g & 1;
+          if (hf == 0) {
+            WT(0, mbar_wait(v_full(vst), vph));
+            bdesc0 = make_smem_desc_sw128(smem_base + kAtSmemV + vst * kAtKVBytes);
+          }
+          const int valid = min(kAtHN, p.N - g * kAtHN);
+          const uint32_t u = hf ? n_h1 : n_h0;
 #pragma unroll
           for (int t = 0; t < kAtQT; ++t) {
-            uint32_t& n_p = (t == 0) ? n_p0 : n_p1;
-            mbar_wait(p_full(t), n_p & 1u);
-            ++n_p;
+            WT(1, mbar_wait(p_full(2 * t + hf), u & 1u));
+            TR(30 + t);
             tc_fence_after();
-            const uint64_t adesc0 = make_smem_desc_sw128(smem_base + kAtSmemP + t * kAtQBytes);
+            // A: half hf = 64 bytes into P_t's 128-byte rows, 32 bytes per 16-key step;
+            // B: 16 keys = 16 rows of 128 B = 2 KB per step (descriptor address field is in 16-byte units)
+            const uint64_t adesc0 = make_smem_desc_sw128(smem_base + kAtSmemP + t * kAtQBytes) + uint64_t(4 * hf);
+            const uint64_t bdesc = bdesc0 + uint64_t(2 * hf * (16 * 128 >> 4));
             const uint32_t d_tmem = tmem_base + kAtTmemO + t * kAtD;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k < ksteps) {
-                // A: 32 B per 16-key step inside P's 128 B rows;
-                // B: 16 keys = 16 rows of 128 B = 2 KB per step (descriptor address field is in 16-byte units)
-                umma_f16_ss<1>(d_tmem, adesc0 + uint64_t(2 * k), bdesc0 + uint64_t(k * (16 * 128 >> 4)), idesc_o,
-                               (j > 0 || k > 0) ? 1u : 0u);
-              }
-            }
-            umma_commit(o_done(t));
+            umma_f16_ss<1>(d_tmem, adesc0, bdesc, idesc_o, g > 0 ? 1u : 0u);
+            if (valid > 16) umma_f16_ss<1>(d_tmem, adesc0 + 2u, bdesc + uint64_t(16 * 128 >> 4), idesc_o, 1u);
+            umma_commit(pv_done(2 * t + hf));
           }
-          umma_commit(v_empty(vst));
-          if (++vst == kAtVStages) { vst = 0; vph ^= 1u; }
+          if (hf) ++n_h1; else ++n_h0;
+          if (hf == 1 || g + 1 == G) {
+            umma_commit(v_empty(vst));
+            if (++vst == kAtVStages) { vst = 0; vph ^= 1u; }
+          }
         }
       }
     }
@@ -256,9 +317,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t pbase = smem_base + kAtSmemP + t * kAtQBytes;
     const uint32_t prow = pbase + uint32_t(r_in_tile * 128);
     const uint32_t swz = uint32_t(r_in_tile & 7);
-    uint32_t n_sf = 0, n_od = 0;
+    uint32_t use0 = 0, use1 = 0;    // uses of half 0 / half 1 so far
     bool store_pending = false;
     const float c = p.scale_log2;
+    const uint64_t c2 = pack_f32x2(c, c);
+    // MUFU turn-taking between warp (t = 0, q) and warp (t = 1, q): named barrier 1 + 2 q + t' is "tile t' may burst"
+    const int bar_mine = 1 + 2 * q + t, bar_other = 1 + 2 * q + (t ^ 1);
+#if MT_ATTN_PINGPONG
+    if (t == 1) pair_bar_arrive(bar_other);   // tile 0 goes first
+#endif
 
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int qp = item % p.num_qp;
@@ -268,22 +335,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       if (row0 >= p.N) {
         // No valid query row in this warp (N = 196: the last warp of the second tile): keep the barrier protocol going,
         // skip all the arithmetic.  Its rows of P_t stay garbage, which only feeds rows of O_t that are never stored.
-        for (int j = 0; j < p.num_kv; ++j) {
-          mbar_wait(s_full(t), n_sf & 1u);
-          ++n_sf;
+        for (int g = 0; g < G; ++g) {
+          const int hf = g & 1;
+          const uint32_t u = hf ? use1 : use0;
+          mbar_wait(s_full(2 * t + hf), u & 1u);
           __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty(t));
-          if (j > 0) { mbar_wait(o_done(t), n_od & 1u); ++n_od; }
+          if (lane == 0) mbar_arrive(s_empty(2 * t + hf));
+          mbar_wait(pv_done(2 * t + hf), (u & 1u) ^ 1u);
           if (store_pending) {
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
             store_pending = false;
           }
+#if MT_ATTN_PINGPONG
+          pair_bar_sync(bar_mine);
+          pair_bar_arrive(bar_other);
+#endif
           __syncwarp();
-          if (lane == 0) mbar_arrive(p_full(t));
+          if (lane == 0) mbar_arrive(p_full(2 * t + hf));
+          if (hf) ++use1; else ++use0;
         }
-        mbar_wait(o_done(t), n_od & 1u);
-        ++n_od;
+        mbar_wait(pv_done(2 * t + 0), (use0 & 1u) ^ 1u);
+        if (use1 > 0) mbar_wait(pv_done(2 * t + 1), (use1 & 1u) ^ 1u);
         continue;
       }
       float m_run = -INFINITY;
@@ -291,195 +364,136 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const uint32_t bh_seed = attn_drop_seed(p.seed_lo, p.seed_hi, uint32_t(bh));
       const uint32_t drop_row = uint32_t(qp * 256 + t * 128 + r_in_tile) * uint32_t(p.N);   // q * N
 
-      for (int j = 0; j < p.num_kv; ++j) {
-        const int valid = min(kAtBN, p.N - j * kAtBN);
-        const int nq = (valid + 15) >> 4;    // 16-key quarters that hold valid keys
-        const int tail = valid & 15;         // valid keys of the last, partially padded quarter (0 = none)
-        mbar_wait(s_full(t), n_sf & 1u);
-        ++n_sf;
-        tc_fence_after();
-#if MT_ATTN_ONE_PASS
-        // whole 64-column score row in registers: S_t is released to the tensor core right after the loads
-        uint32_t s[64];
-        tmem_ld_32x32b_x16_at<0>(ts, s);
-        if (nq > 1) tmem_ld_32x32b_x16_at<16>(ts + 16u, s);
-        if (nq > 2) tmem_ld_32x32b_x16_at<32>(ts + 32u, s);
-        if (nq > 3) tmem_ld_32x32b_x16_at<48>(ts + 48u, s);
+      // one half tile: kC = 32 score columns (16 when the half holds at most 16 valid keys)
+      auto half_step = [&](auto cols_tag, const int g, const int hf, const int valid, const uint32_t u) {
+        constexpr int kC = decltype(cols_tag)::value;
+        uint32_t s[kC];
+        if constexpr (kC == 32) tmem_ld_32x32b_x32(ts + uint32_t(kAtHN * hf), s);
+        else tmem_ld_32x32b_x16(ts + uint32_t(kAtHN * hf), s);
         tmem_wait_ld();
+        TR(3);
+        // the only read of this half of S_t: the tensor core may overwrite it with the scores two halves further on
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(t));
+        if (lane == 0) mbar_arrive(s_empty(2 * t + hf));
         float m_tile = -INFINITY;
+        if (valid < kC) {
 #pragma unroll
-        for (int qi = 0; qi < 4; ++qi) {
-          if (qi < nq) {
-            if (tail != 0 && qi == nq - 1) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (i >= tail) s[16 * qi + i] = 0xff800000u;   // padded keys -> -inf
-                m_tile = fmaxf(m_tile, __uint_as_float(s[16 * qi + i]));
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; i += 2)
-                m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(s[16 * qi + i]), __uint_as_float(s[16 * qi + i + 1])));
-            }
+          for (int i = 0; i < kC; ++i) {
+            if (i >= valid) s[i] = 0xff800000u;   // padded keys -> -inf: exp2 gives 0
+            m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
           }
-        }
-#else
-        // ---- pass 1: row maximum straight from TMEM, one 16-key quarter at a time (a whole 64-column score row plus
-        //      the exp / pack temporaries does not fit the 96 registers a two-CTA-per-SM softmax thread has; TMEM reads
-        //      are cheap, so pass 2 simply loads the quarters again).  Padded keys of the last quarter -> -inf. ----
-        float m_tile = -INFINITY;
-#pragma unroll 1
-        for (int qi = 0; qi < nq; ++qi) {   // rolled on purpose: two resident CTAs share the instruction cache
-          uint32_t sq[16];
-          tmem_ld_32x32b_x16(ts + uint32_t(16 * qi), sq);
-          tmem_wait_ld();
-          if (tail != 0 && qi == nq - 1) {
+        } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) m_tile = fmaxf(m_tile, (i < tail) ? __uint_as_float(sq[i]) : -INFINITY);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; i += 2)
-              m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(sq[i]), __uint_as_float(sq[i + 1])));
-          }
+          for (int i = 0; i < kC; i += 2)
+            m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
         }
-#endif
         // Lazy rescaling: the running maximum is only advanced (and O_t rescaled) when some row of this warp saw its
         // maximum grow by more than 2^kLazyLog2; otherwise the stale maximum keeps being the reference — P may then
         // exceed 1 (by at most 2^kLazyLog2, harmless in fp32 / bf16) and O / l at the end is unchanged mathematically.
         constexpr float kLazyLog2 = 8.0f;
-        const bool grow = (j > 0) && __any_sync(0xffffffffu, (m_tile - m_run) * c > kLazyLog2);
-        const float m_new = (j == 0) ? m_tile : (grow ? fmaxf(m_run, m_tile) : m_run);
+        const bool grow = (g > 0) && __any_sync(0xffffffffu, (m_tile - m_run) * c > kLazyLog2);
+        const float m_new = (g == 0) ? m_tile : (grow ? fmaxf(m_run, m_tile) : m_run);
         const float alpha = grow ? ex2_approx((m_run - m_new) * c) : 1.0f;
         const float mc = m_new * c;
         m_run = m_new;
 
-        // ---- P_t smem and O_t are busy until P_t(j-1)·V_(j-1) has finished.  S_t(j) was issued after that
-        //      MMA and tcgen05 ops retire in order, so this wait never actually blocks. ----
-        if (j > 0) {
-          mbar_wait(o_done(t), n_od & 1u);
-          ++n_od;
+        // this half of P_t is free once the P·V of its previous use has finished (issued two halves ago: never blocks)
+        TR(4);
+        WT(1, mbar_wait(pv_done(2 * t + hf), (u & 1u) ^ 1u));
+        TR(grow ? 6 : 5);
+        if (grow) {
+          // rescale the running output by alpha: no P·V of this tile may be in flight, also not the other half's
+          const uint32_t uo = hf ? use0 : use1;   // >= 1 because g > 0
+          mbar_wait(pv_done(2 * t + (hf ^ 1)), (uo & 1u) ^ 1u);
           tc_fence_after();
-          if (grow) {
-            // rescale the running output by alpha
-            const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+          const uint64_t alpha2 = pack_f32x2(alpha, alpha);
 #pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {
-              uint32_t o[16];
-              tmem_ld_32x32b_x16(to + uint32_t(16 * hh), o);
-              tmem_wait_ld();
+          for (int hh = 0; hh < 4; ++hh) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(to + uint32_t(16 * hh), o);
+            tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                float a0, a1;
-                unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), a0, a1);
-                o[i] = __float_as_uint(a0);
-                o[i + 1] = __float_as_uint(a1);
-              }
-              tmem_st_32x32b_x16(to + uint32_t(16 * hh), o);
+            for (int i = 0; i < 16; i += 2) {
+              float a0, a1;
+              unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), alpha2), a0, a1);
+              o[i] = __float_as_uint(a0);
+              o[i + 1] = __float_as_uint(a1);
             }
-            tmem_wait_st();
+            tmem_st_32x32b_x16(to + uint32_t(16 * hh), o);
           }
+          tmem_wait_st();
+          tc_fence_before();
         }
         if (store_pending) {
           // the previous item's output tile was staged in this warp's rows of P_t
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
+          WT(3, if (lane == 0) tma_store_wait_read<0>(); __syncwarp());
           store_pending = false;
         }
-#if MT_ATTN_ONE_PASS
+        TR(7);
+        // P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V), 8 keys = one 16-byte chunk
         uint64_t l2 = pack_f32x2(0.f, 0.f);   // two partial row sums (even / odd keys), packed fp32x2 adds
-        const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+        const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+#if MT_ATTN_PINGPONG
+        pair_bar_sync(bar_mine);      // my turn on the MUFU pipe
+#endif
 #pragma unroll
-        for (int qi = 0; qi < 4; ++qi) {
-          if (qi < nq) {
+        for (int ch = 0; ch < kC / 8; ++ch) {
+          uint32_t pk[4];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {  // two 16-byte groups (8 keys each) per 16-key quarter
-              uint32_t pk[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float a0, a1;
-                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[16 * qi + 8 * g + 2 * i]),
-                                                  __uint_as_float(s[16 * qi + 8 * g + 2 * i + 1])), c2, nmc2), a0, a1);
-                float e0 = ex2_approx(a0);
-                float e1 = ex2_approx(a1);
-                l2 = add_f32x2(l2, pack_f32x2(e0, e1));
-                if constexpr (kDrop) {
-                  const uint32_t kidx = drop_row + uint32_t(j * kAtBN + 16 * qi + 8 * g + 2 * i);
-                  if (!attn_keep(bh_seed, kidx, p.drop_thresh)) e0 = 0.f;
-                  if (!attn_keep(bh_seed, kidx + 1u, p.drop_thresh)) e1 = 0.f;
-                }
-                pk[i] = pack_bf16x2(e0, e1);
-              }
-              const uint32_t chunk16 = uint32_t(2 * qi + g);
-              const uint32_t addr = prow + ((chunk16 ^ swz) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                           "r"(pk[3])
-                           : "memory");
+          for (int i = 0; i < 4; ++i) {
+            float a0, a1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(s[8 * ch + 2 * i]), __uint_as_float(s[8 * ch + 2 * i + 1])),
+                                   c2, nmc2), a0, a1);
+            float e0 = ex2_approx(a0);
+            float e1 = ex2_approx(a1);
+            l2 = add_f32x2(l2, pack_f32x2(e0, e1));
+            if constexpr (kDrop) {
+              const uint32_t kidx = drop_row + uint32_t(g * kAtHN + 8 * ch + 2 * i);
+              if (!attn_keep(bh_seed, kidx, p.drop_thresh)) e0 = 0.f;
+              if (!attn_keep(bh_seed, kidx + 1u, p.drop_thresh)) e1 = 0.f;
             }
+            pk[i] = pack_bf16x2(e0, e1);
           }
+          const uint32_t chunk16 = uint32_t(4 * hf + ch);
+          const uint32_t addr = prow + ((chunk16 ^ swz) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                       "r"(pk[3])
+                       : "memory");
         }
-#else
-        // ---- pass 2: P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V) ----
-        uint64_t l2 = pack_f32x2(0.f, 0.f);   // two partial row sums (even / odd keys), packed fp32x2 adds
-        const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
-#pragma unroll 1
-        for (int qi = 0; qi < nq; ++qi) {
-          {
-            uint32_t sq[16];
-            tmem_ld_32x32b_x16(ts + uint32_t(16 * qi), sq);
-            tmem_wait_ld();
-            if (qi == nq - 1) {
-              // the last read of S_t: the tensor core may overwrite it with the next tile's scores
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_empty(t));
-              if (tail != 0) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (i >= tail) sq[i] = 0xff800000u;   // -inf: exp2 gives 0 for the padded keys
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {  // two 16-byte groups (8 keys each) per 16-key quarter
-              uint32_t pk[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float a0, a1;
-                unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sq[8 * g + 2 * i]), __uint_as_float(sq[8 * g + 2 * i + 1])),
-                                       c2, nmc2), a0, a1);
-                float e0 = ex2_approx(a0);
-                float e1 = ex2_approx(a1);
-                l2 = add_f32x2(l2, pack_f32x2(e0, e1));
-                if constexpr (kDrop) {
-                  const uint32_t kidx = drop_row + uint32_t(j * kAtBN + 16 * qi + 8 * g + 2 * i);
-                  if (!attn_keep(bh_seed, kidx, p.drop_thresh)) e0 = 0.f;
-                  if (!attn_keep(bh_seed, kidx + 1u, p.drop_thresh)) e1 = 0.f;
-                }
-                pk[i] = pack_bf16x2(e0, e1);
-              }
-              const uint32_t chunk16 = uint32_t(2 * qi + g);
-              const uint32_t addr = prow + ((chunk16 ^ swz) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                           "r"(pk[3])
-                           : "memory");
-            }
-          }
-        }
+#if MT_ATTN_PINGPONG
+        pair_bar_arrive(bar_other);   // the other tile's turn
 #endif
         float l_lo, l_hi;
         unpack_f32x2(l2, l_lo, l_hi);
         l_run = fmaf(l_run, alpha, l_lo + l_hi);
+        TR(8);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(t));
+        if (lane == 0) mbar_arrive(p_full(2 * t + hf));
+        TR(9);
+      };
+
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        const int hf = g & 1;
+        const int valid = min(kAtHN, p.N - g * kAtHN);
+        const uint32_t u = hf ? use1 : use0;
+        TR(1);
+        WT(0, mbar_wait(s_full(2 * t + hf), u & 1u));
+        TR(2);
+        tc_fence_after();
+        if (valid > 16) half_step(std::integral_constant<int, 32>{}, g, hf, valid, u);
+        else half_step(std::integral_constant<int, 16>{}, g, hf, valid, u);
+        if (hf) ++use1; else ++use0;
       }
 
       // ---- epilogue: O_t / l -> bf16 -> staged in this warp's rows of P_t -> TMA store ----
-      mbar_wait(o_done(t), n_od & 1u);
-      ++n_od;
+      TR(10);
+      WT(2, mbar_wait(pv_done(2 * t + 0), (use0 & 1u) ^ 1u));
+      if (use1 > 0) WT(2, mbar_wait(pv_done(2 * t + 1), (use1 & 1u) ^ 1u));
+      TR(11);
       tc_fence_after();
       const float inv_l = p.drop_scale / l_run;
       const uint64_t inv_l2 = pack_f32x2(inv_l, inv_l);
@@ -514,12 +528,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tma_store_4d(&tm_out, pbase + uint32_t(32 * q * 128), 0, h, row0, b);
         tma_store_commit();
       }
+      TR(12);
       store_pending = true;
     }
     if (lane == 0) tma_store_wait_all<0>();
     __syncwarp();
+#if MT_ATTN_PINGPONG
+    if (t == 0) pair_bar_sync(bar_mine);   // consume tile 1's last hand-over: no barrier is left half-armed
+#endif
   }
 
+#if MT_ATTN_TRACE == 2
+  if (p.trace != nullptr && blockIdx.x < 4 && lane == 0) {
+    long long* o = p.trace + (size_t(blockIdx.x) * 12 + warp) * 8;
+    o[0] = wt0; o[1] = wt1; o[2] = wt2; o[3] = wt3; o[4] = clock64() - wt_begin;
+  }
+#endif
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -531,6 +555,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 namespace mt {
 int attention_generic_fwd(const void* qkv, void* out, int B, int N, int H, int dh, float scale, cudaStream_t s);
+}
+
+// MT_ATTN_TRACE builds: device buffer of 2 x 12 x 1024 int64 that the next launches log into (nullptr = off)
+static long long* g_attn_trace = nullptr;
+extern "C" int mt_attention_set_trace(void* buf) {
+  g_attn_trace = reinterpret_cast<long long*>(buf);
+  return MT_ATTN_TRACE ? -MT_ATTN_TRACE : 1;   // 1: this build has no trace points; -1 event log, -2 wait accounting
 }
 
 static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, int N, int H, int dh, float scale,
@@ -573,10 +604,12 @@ static int attention_fwd_impl(const void* qkv, void* out, float* lse2, int B, in
   p.B = B; p.N = N; p.H = H;
   p.num_qp = ceil_div(N, 256);
   p.num_kv = ceil_div(N, kAtBN);
+  p.num_half = ceil_div(N, kAtHN);
   p.num_items = B * H * p.num_qp;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse2 = lse2;
   p.tl = timeline_next_slot();
+  p.trace = g_attn_trace;
   p.drop_thresh = drop_p > 0.f ? uint32_t(double(drop_p) * 4294967296.0) : 0u;
   p.drop_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
   p.seed_lo = uint32_t(seed);

@@ -24,6 +24,9 @@
 // warps 4..19 = epilogue (warp%4 selects the TMEM lane quarter, (warp-4)/4 the 64-column quarter of the tile).
 // a timed-out barrier wait traps without the device printf (the call sequence costs registers in every role)
 #define MT_WAIT_QUIET 1
+#ifndef MT_GEMM_TRACE
+#define MT_GEMM_TRACE 0   // 1: debugging build that counts the cycles every warp of CTAs 0-3 spends in its barrier waits
+#endif
 #include "mt_ptx.cuh"
 #include "mt_common.cuh"
 #include <stdlib.h>
@@ -52,13 +55,19 @@ enum : int {
   kEpiRes = 3,       // bias + residual (hi [+ lo]) -> hi [+ lo] output + LayerNorm row sums     (proj, fc2)
 };
 
+#ifndef MT_GEMM_PF_DIST
+#define MT_GEMM_PF_DIST 16   // k-blocks (64 columns of K each) the A-operand L2 prefetch runs ahead of the TMA loads; 0 = off
+#endif
+#ifndef MT_GEMM_STAGES_CG2
+#define MT_GEMM_STAGES_CG2 5   // operand ring depth of the 2-CTA kernel (experiment knob: tools/build_variant.py)
+#endif
 template <int CG, bool HILO>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;                       // 16 KB
   static constexpr int kBRows = (CG == 2) ? kBN / 2 : kBN;            // rows of W this CTA loads
   static constexpr int kBBytes = kBRows * kBK * 2;                    // 16 / 32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CG == 2) ? 5 : 3;
+  static constexpr int kStages = (CG == 2) ? MT_GEMM_STAGES_CG2 : 3;
   // per warp: 32 rows x 32 columns bf16 (one 2 KB TMA store per 32-column slice), or — split stream — 32 rows x 16
   // columns of hi + the same of lo (two 1 KB stores per 16-column piece)
   static constexpr int kEpiStageBytes = 2048;
@@ -101,6 +110,7 @@ struct GemmParams {
   unsigned long long* tl;       // optional timeline slot {first CTA start, last CTA end} in globaltimer ns, or nullptr
   int fp8;                      // operands are e4m3 bytes (kind::f8f6f4, 128 elements of K per swizzle row); generic epilogue
   float acc_scale;              // the accumulator is multiplied by this before the bias (fp8: scale_x * scale_w; else 1)
+  long long* trace;             // MT_GEMM_TRACE builds only (tools/gemm_trace.py): per-warp wait-cycle counters
   __nv_bfloat16* y_direct;      // != nullptr: the epilogue writes its bf16 results straight from registers (one 32-byte
   __nv_bfloat16* ylo_direct;    // sector per thread and 16-column piece) instead of staging them in shared memory for a
                                 // TMA store: the staging write + TMA read of every tile competes with the operand
@@ -221,6 +231,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   timeline_start(p.tl);
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;   // work items: (tile, K split), split fastest
+#if MT_GEMM_TRACE
+  long long wt0 = 0, wt1 = 0, wt2 = 0, wt3 = 0;
+  const long long wt_begin = clock64();
+#define WT(slot, stmt)                                   \
+  do {                                                   \
+    const long long a_ = clock64();                      \
+    stmt;                                                \
+    wt##slot += clock64() - a_;                          \
+  } while (0)
+#else
+#define WT(slot, stmt) do { stmt; } while (0)
+#endif
   const int kbk = (MODE == kEpiGeneric && p.fp8) ? 2 * kBK : kBK;      // elements of K per 128-byte swizzle row
   const int num_kb = (p.K + kbk - 1) / kbk;
 
@@ -234,6 +256,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_leader_base = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
+      // L2 prefetch of the A operand, MT_GEMM_PF_DIST k-blocks ahead of the loads (across tile boundaries): the
+      // activations stream in from HBM, and with only kStages x 32 KB in flight per SM the ~2 us HBM latency left the MMA
+      // issuer waiting for operands a third of the time (tools/gemm_trace.py: 34 % at 5 stages, 41 % at 4, 53 % at 3);
+      // the weights are L2-resident after the first wave and need none.
+      const bool pf_on = !(MODE == kEpiGeneric && p.mn_major) && MT_GEMM_PF_DIST > 0;
+      int pf_t = cluster_id, pf_kb = 0, pf_kb_end = 0, pf_row = 0;
+      auto pf_enter_tile = [&]() {
+        if (pf_t < num_tiles) {
+          const int tile_ = pf_t / p.split_k, split_ = pf_t - tile_ * p.split_k;
+          pf_row = (tile_ / p.num_n_tiles) * (kBM * CG) + int(rank) * kBM;
+          pf_kb = split_ * p.kb_per_split;
+          pf_kb_end = min(num_kb, pf_kb + p.kb_per_split);
+        }
+      };
+      auto pf_step = [&](bool issue) {
+        if (pf_t >= num_tiles) return;
+        if (issue) tma_prefetch_l2_2d(&tm_a, pf_kb * kbk, pf_row);
+        if (++pf_kb >= pf_kb_end) {
+          pf_t += num_clusters;
+          pf_enter_tile();
+        }
+      };
+      if (pf_on) {
+        pf_enter_tile();
+        // the first kStages k-blocks are requested by the loads themselves right away: prefetch only beyond them
+        for (int i = 0; i < MT_GEMM_PF_DIST; ++i) pf_step(i >= Cfg::kStages);
+      }
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int tile = t / p.split_k, split = t - tile * p.split_k;
         const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
@@ -241,7 +290,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int row_b = n_tile * kBN + ((CG == 2) ? int(rank) * (kBN / 2) : 0);
         const int kb_begin = split * p.kb_per_split, kb_end = min(num_kb, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          WT(0, mbar_wait(empty_bar(stage), phase ^ 1u));
+          if (pf_on) pf_step(true);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           if (MODE == kEpiGeneric && p.mn_major) {
@@ -296,13 +346,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int as = 0;
       uint32_t aphase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);  // epilogue drained this accumulator stage
+        WT(0, mbar_wait(tempty_bar(as), aphase ^ 1u));  // epilogue drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * kBN);
         const int split = t % p.split_k;
         const int kb_begin = split * p.kb_per_split, kb_end = min(num_kb, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          WT(1, mbar_wait(full_bar(stage), phase));
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint64_t adesc = mnm ? make_smem_desc_sw128(sa, 1024, 8192) : make_smem_desc_sw128(sa);
@@ -374,6 +424,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     float4 bias_pf = load_bias(cluster_id);
     float2 stat_pf = load_stat(cluster_id);
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+#if MT_GEMM_TRACE
+      const long long tile_top = clock64();
+#endif
       const int tile = t / p.split_k;
       const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
       const int row0 = m_tile * (kBM * CG) + int(rank) * kBM + 32 * q;  // first row of this warp
@@ -488,7 +541,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           load_hi(0, rh[0]);
         }
       }
-      mbar_wait(tfull_bar(as), aphase);
+#if MT_GEMM_TRACE
+      wt2 += clock64() - tile_top;
+#endif
+      WT(0, mbar_wait(tfull_bar(as), aphase));
+#if MT_GEMM_TRACE
+      const long long pieces_top = clock64();
+#endif
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(32 * q) << 16) + uint32_t(as * kBN + kEpiCols * cq);
 #pragma unroll
@@ -609,8 +668,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if constexpr (kHiLo) {
           // split stream: one 32-row x 16-column box of hi and one of lo per piece
           if (store_pending) {
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
+            WT(1, if (lane == 0) tma_store_wait_read<0>(); __syncwarp());
             store_pending = false;
           }
 #pragma unroll
@@ -632,8 +690,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         } else {
           if ((piece & 1) == 0 && store_pending) {
             // staging buffer is about to be overwritten: the previous TMA store must have read it
-            if (lane == 0) tma_store_wait_read<0>();
-            __syncwarp();
+            WT(1, if (lane == 0) tma_store_wait_read<0>(); __syncwarp());
             store_pending = false;
           }
           // 64B-swizzled store into the staging tile: row = lane, 32 bytes of this piece = chunks 2*(piece&1), +1
@@ -662,6 +719,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         float4* dst = reinterpret_cast<float4*>(p.out_row_sums) + size_t(row) * ((p.N + 63) >> 6) + (col0 >> 6);
         *dst = make_float4(shift, a0 + a1, q0 + q1, 0.f);
       }
+#if MT_GEMM_TRACE
+      wt3 += clock64() - pieces_top;
+#endif
       if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -669,6 +729,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 
   // ---- teardown ----
+#if MT_GEMM_TRACE
+  if (p.trace != nullptr && blockIdx.x < 4 && lane == 0) {
+    long long* o = p.trace + (size_t(blockIdx.x) * (kGemmThreads / 32) + warp) * 8;
+    o[0] = wt0; o[1] = wt1; o[2] = wt2; o[3] = wt3; o[4] = clock64() - wt_begin;
+  }
+#endif
   __syncwarp();  // re-converge the single-lane role loops before the aligned barrier
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -679,6 +745,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// MT_GEMM_TRACE builds: device buffer of 4 x 20 x 8 int64 that the next GEMM launch fills (nullptr = off)
+static long long* g_gemm_trace = nullptr;
+extern "C" int mt_gemm_set_trace(void* buf) {
+  g_gemm_trace = reinterpret_cast<long long*>(buf);
+  return MT_GEMM_TRACE ? -1 : 1;   // 1: this build has no counters
+}
+
 struct GemmCall {
   const void* x; const void* w; const float* bias;
   const void* resid; const void* resid_lo; int ldr;
@@ -763,6 +836,7 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   p.fp8 = c.fp8;
   p.acc_scale = c.fp8 ? c.acc_scale : 1.0f;
   p.tl = timeline_next_slot();
+  p.trace = g_gemm_trace;
   {
     // MT_B200_EPI_DIRECT: 1 = every bf16 output leaves the epilogue as 32-byte register stores, 0 = staged + TMA store
     static int direct = -1;
@@ -789,6 +863,15 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   if (rc) return rc;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   int clusters = sms / CG;
+  {
+    // experiment knob (tools/bench_kernels.py): run on fewer CTA clusters, to tell per-SM limits from chip-wide ones
+    static int cap = -1;
+    if (cap < 0) {
+      const char* e = getenv("MT_B200_GEMM_MAX_CLUSTERS");
+      cap = (e && atoi(e) > 0) ? atoi(e) : 0;
+    }
+    if (cap > 0 && clusters > cap) clusters = cap;
+  }
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
 

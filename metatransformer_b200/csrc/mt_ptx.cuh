@@ -101,6 +101,12 @@ MT_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
 MT_DEVINL void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
+// pull one box of a tiled tensor into L2 (no shared-memory destination, no barrier): the later cp.async.bulk.tensor of
+// the same box then sees the L2 hit latency instead of the HBM one
+MT_DEVINL void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
+}
 // L2 cache-policy descriptors (same encodings CUTLASS ships as TMA::CacheHintSm90)
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
@@ -199,6 +205,18 @@ MT_DEVINL void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M x 16, K-major) is read from tensor memory — row m = lane m, two
+// 16-bit elements per 32-bit column (8 columns per instruction) — instead of shared memory.  With both operands in
+// shared memory an M = 128 instruction occupies the tensor pipe for >= ~60 cycles however small N is (the A tile is
+// re-read from shared memory every time); from tensor memory the floor is N / 2 cycles (tools/bench_umma.cu).
+MT_DEVINL void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
 }
 // same with fp8 (e4m3 / e5m2, chosen in the instruction descriptor) operands: 32 elements of K per instruction
 template <int CG>
@@ -408,6 +426,35 @@ MT_DEVINL bool attn_keep(uint32_t bh_seed, uint32_t idx, uint32_t thresh) { retu
 
 MT_DEVINL void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+MT_DEVINL void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// 64-thread barriers 1..8 with immediate ids: a register id makes ptxas reserve all 16 hardware barriers for the CTA
+// (launch__occupancy_limit_barriers), immediates only the ones named
+MT_DEVINL void pair_bar_sync(int id) {
+  switch (id) {
+    case 1: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    case 5: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+    case 6: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
+    case 7: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
+  }
+}
+MT_DEVINL void pair_bar_arrive(int id) {
+  switch (id) {
+    case 1: asm volatile("bar.arrive 1, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.arrive 2, 64;" ::: "memory"); break;
+    case 3: asm volatile("bar.arrive 3, 64;" ::: "memory"); break;
+    case 4: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
+    case 5: asm volatile("bar.arrive 5, 64;" ::: "memory"); break;
+    case 6: asm volatile("bar.arrive 6, 64;" ::: "memory"); break;
+    case 7: asm volatile("bar.arrive 7, 64;" ::: "memory"); break;
+    default: asm volatile("bar.arrive 8, 64;" ::: "memory"); break;
+  }
 }
 
 }  // namespace mt

@@ -121,7 +121,8 @@ def test_layernorm_folded_gemm_matches_oracle(mt, M, N, K, gelu):
     _assert_close(y, ref, what=f"LN-folded gemm {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("B,N,H", [(1, 1, 1), (2, 17, 2), (1, 128, 1), (2, 196, 3), (1, 256, 2), (1, 257, 1),
+@pytest.mark.parametrize("B,N,H", [(1, 1, 1), (1, 16, 1), (2, 17, 2), (1, 32, 2), (1, 33, 1), (1, 49, 2), (1, 64, 1),
+                                   (1, 80, 1), (1, 97, 1), (1, 128, 1), (2, 196, 3), (1, 256, 2), (1, 257, 1),
                                    (2, 512, 2), (1, 1568, 2)])
 def test_attention_matches_oracle(mt, B, N, H):
     g = torch.Generator().manual_seed(N + H)
