@@ -20,12 +20,6 @@
 //     one pass, nothing is read from TMEM twice;
 //   * online softmax in fp32 registers with lazy rescaling, exp2 with the scale*log2(e) factor folded in; P goes back
 //     as bf16 through the 128B-swizzled P_t tile (half h = 64 bytes of every row), P_t-half·V is issued per half;
-//   * the exponentials are a pure MUFU burst (32 ex2 per thread and half) and the MUFU pipe arbitrates per instruction,
-//     so the four softmax warps of a scheduler drift into a convoy: all burst together at a quarter of the rate each,
-//     then all do their barrier / tcgen05.ld / max work together while the MUFU pipe idles (39 % MUFU-active in the
-//     round-2 capture, with per-half times that were the SUM of the phases).  The two warps of a CTA that share a
-//     scheduler (same lane quarter of tile 0 and tile 1) therefore take turns for the burst through a pair of named
-//     barriers: one computes exponentials while the other waits for / loads / reduces its next scores;
 //   * K/V tiles (64 keys = two halves) stream through 3- / 2-stage TMA rings shared by both query tiles; the last half
 //     of a row of keys runs at N = 16 when it holds at most 16 valid keys (N = 196: 4 keys).
 //
@@ -33,9 +27,6 @@
 // 9 = S=QK^T issuer + TMEM allocator, 10 = O+=PV issuer, 11 idle (completes the third warpgroup for setmaxnreg).
 // a timed-out barrier wait traps without the device printf: the call sequence costs the 40-register role warps spills
 #define MT_WAIT_QUIET 1
-#ifndef MT_ATTN_PINGPONG
-#define MT_ATTN_PINGPONG 0   // 1: A/B builds with MUFU turn-taking between the two query tiles (measured 2-9 % slower)
-#endif
 #ifndef MT_ATTN_TRACE
 #define MT_ATTN_TRACE 0   // 1: debugging build that logs (clock64 << 8 | event id) per warp for the first two CTAs
 #endif
@@ -321,11 +312,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     bool store_pending = false;
     const float c = p.scale_log2;
     const uint64_t c2 = pack_f32x2(c, c);
-    // MUFU turn-taking between warp (t = 0, q) and warp (t = 1, q): named barrier 1 + 2 q + t' is "tile t' may burst"
-    const int bar_mine = 1 + 2 * q + t, bar_other = 1 + 2 * q + (t ^ 1);
-#if MT_ATTN_PINGPONG
-    if (t == 1) pair_bar_arrive(bar_other);   // tile 0 goes first
-#endif
 
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const int qp = item % p.num_qp;
@@ -347,10 +333,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             __syncwarp();
             store_pending = false;
           }
-#if MT_ATTN_PINGPONG
-          pair_bar_sync(bar_mine);
-          pair_bar_arrive(bar_other);
-#endif
           __syncwarp();
           if (lane == 0) mbar_arrive(p_full(2 * t + hf));
           if (hf) ++use1; else ++use0;
@@ -434,9 +416,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         // P = exp2(S*c - m*c) -> bf16 -> 128B-swizzled smem (A operand of P·V), 8 keys = one 16-byte chunk
         uint64_t l2 = pack_f32x2(0.f, 0.f);   // two partial row sums (even / odd keys), packed fp32x2 adds
         const uint64_t nmc2 = pack_f32x2(-mc, -mc);
-#if MT_ATTN_PINGPONG
-        pair_bar_sync(bar_mine);      // my turn on the MUFU pipe
-#endif
 #pragma unroll
         for (int ch = 0; ch < kC / 8; ++ch) {
           uint32_t pk[4];
@@ -461,9 +440,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                        "r"(pk[3])
                        : "memory");
         }
-#if MT_ATTN_PINGPONG
-        pair_bar_arrive(bar_other);   // the other tile's turn
-#endif
         float l_lo, l_hi;
         unpack_f32x2(l2, l_lo, l_hi);
         l_run = fmaf(l_run, alpha, l_lo + l_hi);
@@ -533,9 +509,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
     if (lane == 0) tma_store_wait_all<0>();
     __syncwarp();
-#if MT_ATTN_PINGPONG
-    if (t == 0) pair_bar_sync(bar_mine);   // consume tile 1's last hand-over: no barrier is left half-armed
-#endif
   }
 
 #if MT_ATTN_TRACE == 2

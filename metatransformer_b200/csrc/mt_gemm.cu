@@ -55,9 +55,6 @@ enum : int {
   kEpiRes = 3,       // bias + residual (hi [+ lo]) -> hi [+ lo] output + LayerNorm row sums     (proj, fc2)
 };
 
-#ifndef MT_GEMM_PF_DIST
-#define MT_GEMM_PF_DIST 16   // k-blocks (64 columns of K each) the A-operand L2 prefetch runs ahead of the TMA loads; 0 = off
-#endif
 #ifndef MT_GEMM_STAGES_CG2
 #define MT_GEMM_STAGES_CG2 5   // operand ring depth of the 2-CTA kernel (experiment knob: tools/build_variant.py)
 #endif
@@ -256,33 +253,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full_leader_base = (CG == 2) ? mapa_u32(full_bar(0), 0) : full_bar(0);
-      // L2 prefetch of the A operand, MT_GEMM_PF_DIST k-blocks ahead of the loads (across tile boundaries): the
-      // activations stream in from HBM, and with only kStages x 32 KB in flight per SM the ~2 us HBM latency left the MMA
-      // issuer waiting for operands a third of the time (tools/gemm_trace.py: 34 % at 5 stages, 41 % at 4, 53 % at 3);
-      // the weights are L2-resident after the first wave and need none.
-      const bool pf_on = !(MODE == kEpiGeneric && p.mn_major) && MT_GEMM_PF_DIST > 0;
-      int pf_t = cluster_id, pf_kb = 0, pf_kb_end = 0, pf_row = 0;
-      auto pf_enter_tile = [&]() {
-        if (pf_t < num_tiles) {
-          const int tile_ = pf_t / p.split_k, split_ = pf_t - tile_ * p.split_k;
-          pf_row = (tile_ / p.num_n_tiles) * (kBM * CG) + int(rank) * kBM;
-          pf_kb = split_ * p.kb_per_split;
-          pf_kb_end = min(num_kb, pf_kb + p.kb_per_split);
-        }
-      };
-      auto pf_step = [&](bool issue) {
-        if (pf_t >= num_tiles) return;
-        if (issue) tma_prefetch_l2_2d(&tm_a, pf_kb * kbk, pf_row);
-        if (++pf_kb >= pf_kb_end) {
-          pf_t += num_clusters;
-          pf_enter_tile();
-        }
-      };
-      if (pf_on) {
-        pf_enter_tile();
-        // the first kStages k-blocks are requested by the loads themselves right away: prefetch only beyond them
-        for (int i = 0; i < MT_GEMM_PF_DIST; ++i) pf_step(i >= Cfg::kStages);
-      }
+      // tools/gemm_trace.py shows the MMA issuer waiting for operands 25-35 % of the time on every layer shape, the same
+      // at 74 and at 37 clusters (a per-SM limit) and falling with ring depth (53 % / 41 % / 34 % at 3 / 4 / 5 stages).
+      // tools/bench_tma.cu puts a number on it: one SM's TMA unit delivers 37 B/clk of 128-byte rows (870 cycles per
+      // 32 KB stage, on 2 SMs and on 148 alike; 46-48 B/clk when half of the boxes arrive by cluster multicast), a
+      // 128 x 256 tile per SM needs 64 B/clk.  Two attempts to go around it lost and were removed: prefetching A into
+      // L2 16 / 32 k-blocks ahead (operand waits 42 %, +4-7 % time: the prefetches queue in the same TMA unit) and
+      // copying A with cp.async from a loader warp (2.3x slower: at most ring-depth x 16 KB in flight per SM).
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int tile = t / p.split_k, split = t - tile * p.split_k;
         const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
@@ -291,7 +268,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int kb_begin = split * p.kb_per_split, kb_end = min(num_kb, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           WT(0, mbar_wait(empty_bar(stage), phase ^ 1u));
-          if (pf_on) pf_step(true);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           if (MODE == kEpiGeneric && p.mn_major) {

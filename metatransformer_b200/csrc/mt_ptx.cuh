@@ -101,12 +101,6 @@ MT_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
 MT_DEVINL void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
-// pull one box of a tiled tensor into L2 (no shared-memory destination, no barrier): the later cp.async.bulk.tensor of
-// the same box then sees the L2 hit latency instead of the HBM one
-MT_DEVINL void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
-}
 // L2 cache-policy descriptors (same encodings CUTLASS ships as TMA::CacheHintSm90)
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
@@ -429,32 +423,6 @@ MT_DEVINL void named_bar_sync(int id, int nthreads) {
 }
 MT_DEVINL void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-// 64-thread barriers 1..8 with immediate ids: a register id makes ptxas reserve all 16 hardware barriers for the CTA
-// (launch__occupancy_limit_barriers), immediates only the ones named
-MT_DEVINL void pair_bar_sync(int id) {
-  switch (id) {
-    case 1: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-    case 3: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-    case 4: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    case 5: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
-    case 6: asm volatile("bar.sync 6, 64;" ::: "memory"); break;
-    case 7: asm volatile("bar.sync 7, 64;" ::: "memory"); break;
-    default: asm volatile("bar.sync 8, 64;" ::: "memory"); break;
-  }
-}
-MT_DEVINL void pair_bar_arrive(int id) {
-  switch (id) {
-    case 1: asm volatile("bar.arrive 1, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.arrive 2, 64;" ::: "memory"); break;
-    case 3: asm volatile("bar.arrive 3, 64;" ::: "memory"); break;
-    case 4: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
-    case 5: asm volatile("bar.arrive 5, 64;" ::: "memory"); break;
-    case 6: asm volatile("bar.arrive 6, 64;" ::: "memory"); break;
-    case 7: asm volatile("bar.arrive 7, 64;" ::: "memory"); break;
-    default: asm volatile("bar.arrive 8, 64;" ::: "memory"); break;
-  }
 }
 
 }  // namespace mt
