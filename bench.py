@@ -315,7 +315,13 @@ def run_ours(args):
                 "traffic": None if traffic is None else traffic.get("gemm_mean_bytes_per_launch"),
                 "traffic_source": None if traffic is None else traffic.get("source"),
                 "probe": {"how": f"device timeline of one graph replay after {settle} back-to-back replays "
-                                 f"({settle * ms_total / args.steps * 1e-3:.1f} s)", "clocks": pclocks}}
+                                 f"({settle * ms_total / args.steps * 1e-3:.1f} s)", "clocks": pclocks},
+                # what actually caps the main loop (profiles/r2_gemm_waits.md; constants measured with
+                # tools/gemm_trace.py and tools/bench_tma.cu, not re-measured by this run)
+                "limiter": {"what": "per-SM TMA operand ingest", "needed_B_per_clk_per_sm": 64.0,
+                            "delivered_B_per_clk_per_sm": 43.5, "tma_microbench_B_per_clk_per_sm": 37.4,
+                            "mma_issuer_operand_wait_share": {"qkv": 0.34, "fc1": 0.28, "proj": 0.30, "fc2": 0.27},
+                            "source": "profiles/r2_gemm_waits.md"}}
         attn_bytes = 4.0 * M * D * 2          # read q, k, v once + write the output once, bf16
         attn_us = kinds["attention"]["mean"]
         roof_others = [{"kernel": "attention_fwd_kernel (%d launches/step)" % kinds["attention"]["launches"], "bound": "hbm",
@@ -323,7 +329,9 @@ def run_ours(args):
                         "frac": attn_bytes / (attn_us * 1e-6) / 1e9 / hbm_gbs, "avg_launch_ms": attn_us * 1e-3,
                         "algorithmic_bytes_per_launch": attn_bytes,
                         "traffic": None if traffic is None else traffic.get("attention_bytes_per_launch"),
-                        "note": "also MUFU-bound: one ex2 per score, 16 / clk / SM puts the same ~47 us floor under it"}]
+                        "note": "also MUFU-bound: one ex2 per score, 16 / clk / SM puts the same ~47 us floor under it; "
+                                "in-kernel wait accounting (profiles/r2_attention_trace.md): latency-bound dependency cycle, "
+                                "no unit saturated"}]
         step_timeline = {k: res["summary"][k] for k in ("kernels", "span_us", "sum_kernel_us", "sum_gap_us", "mean_gap_us",
                                                         "max_gap_us")}
         step_timeline["by_kind_us"] = {k: round(v["total"], 2) for k, v in kinds.items()}
