@@ -67,13 +67,29 @@ MT_DEVINL void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
       "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(cta) : "memory");
 }
+// Suspend-time hint of mbarrier.try_wait: a waiting thread sleeps until the phase completes (or the hint expires) instead
+// of coming back every few tens of nanoseconds (without a hint the limit measured here is one poll per ~40 ns: the 16
+// epilogue warps of a GEMM CTA and the issuer threads spin through 40-60 % of a kernel).  Same-call A/B, 2000 ns against
+// none: C2 step 9.79 / 9.83 ms against 9.94 / 10.20, fc1 220 us against 226, qkv 154 against 156, attention 92.1 against
+// 92.9 — fewer wasted issue slots and less power under the cap.  0 = no hint.
+#ifndef MT_WAIT_HINT_NS
+#define MT_WAIT_HINT_NS 2000
+#endif
 MT_DEVINL uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if MT_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(uint32_t(MT_WAIT_HINT_NS)) : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
   return ok;
 }
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.  try_wait itself suspends the
