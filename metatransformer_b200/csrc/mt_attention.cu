@@ -6,18 +6,19 @@
 // Blackwell design (sm_100a only), head_dim = 64, no mask, optional attention dropout:
 //   * q, k, v are read straight out of the packed (B, N, 3, H, 64) qkv buffer through one 4-D TMA descriptor
 //     (no permute / contiguous copies), output is written straight into (B, N, H*64) through a 4-D TMA store;
-//   * persistent CTAs, TWO per SM (108 KB of shared memory, 256 TMEM columns, 96 registers per softmax thread each):
-//     the kernel is bound by MUFU (one ex2 per score: 16 / clk / SM is the same 47 us floor as the HBM traffic at C2)
-//     and by the softmax warps' instruction latency, so what counts is how many independent softmax instruction streams
-//     an SM scheduler can pick from (4 warps per scheduler) and that none of them ever waits for the tensor core;
+//   * persistent CTAs, TWO per SM (108 KB of shared memory, 256 TMEM columns, compiled for 80 registers per thread):
+//     no unit is saturated at C2 (MUFU 40 %, issue slots 50 %, tensor pipe 23 %: profiles/r2_attention_trace.md) — the
+//     kernel is a dependency cycle between the softmax warps and the two single-thread MMA issuers whose steps cost
+//     latency, so what counts is how many independent softmax instruction streams an SM scheduler can pick from
+//     (4 warps per scheduler) and that none of them waits for the tensor core longer than it must;
 //   * a work item is (batch, head, 256 query rows) = two 128-row query tiles that ping-pong; warps whose 32 query rows
 //     all lie beyond N only keep the barrier protocol going;
 //   * S = Q·K^T and O += P·V are tcgen05.mma (bf16 in, fp32 accumulate) with S and O living in TMEM.  The unit of the
-//     softmax pipeline is a HALF key tile of 32 keys: S_t has two 32-column halves (TMEM columns 64 t + 32 h) that are
-//     computed by separate N = 32 MMAs with their own barriers.  A softmax thread (one query row) pulls its 32 scores
-//     with ONE tcgen05.ld, releases the half immediately (the issuer then computes the scores two halves ahead into
-//     it while the warp is busy with the exponentials) and does max / exp2 / row sum / bf16 pack from registers —
-//     one pass, nothing is read from TMEM twice;
+//     softmax pipeline is a HALF key tile of 32 keys: S_t has two 32-column halves (TMEM columns 64 t + 32 h) with their
+//     own barriers (both halves of a key tile are produced by one N = 64 MMA group: a single-thread tcgen05.mma costs
+//     60-105 cycles to issue whatever N is).  A softmax thread (one query row) pulls its 32 scores with ONE tcgen05.ld,
+//     releases the half immediately and does max / exp2 / row sum / bf16 pack from registers — one pass, nothing is
+//     read from TMEM twice;
 //   * online softmax in fp32 registers with lazy rescaling, exp2 with the scale*log2(e) factor folded in; P goes back
 //     as bf16 through the 128B-swizzled P_t tile (half h = 64 bytes of every row), P_t-half·V is issued per half;
 //   * K/V tiles (64 keys = two halves) stream through 3- / 2-stage TMA rings shared by both query tiles; the last half
@@ -174,8 +175,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #define WT(slot, stmt) do { stmt; } while (0)
 #endif
 
-  // register re-distribution between warpgroups (compiled for 80/thread: two CTAs per SM): the softmax warpgroups hold
-  // a 32-column score row per thread plus the exp / pack temporaries, the loader / MMA warpgroup needs almost nothing
+  // register re-distribution between warpgroups (the code is compiled for 80 registers per thread: two CTAs per SM; the
+  // run-time split only returns the role warpgroup's share to the pool): the softmax warpgroups hold a 32-column score
+  // row per thread plus the exp / pack temporaries, the loader / MMA warpgroup needs almost nothing
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
