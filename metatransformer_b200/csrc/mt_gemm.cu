@@ -814,13 +814,18 @@ static int launch_gemm(const GemmCall& c, cudaStream_t stream) {
   p.tl = timeline_next_slot();
   p.trace = g_gemm_trace;
   {
-    // MT_B200_EPI_DIRECT: 1 = every bf16 output leaves the epilogue as 32-byte register stores, 0 = staged + TMA store
-    static int direct = -1;
-    if (direct < 0) {
+    // Output path of the epilogue: staged in shared memory + TMA store, or 32-byte register stores straight to global
+    // memory.  Direct stores lose wherever the epilogue is the slower side (qkv 196 vs 163 us, proj 115 vs 103, fc1 267
+    // vs 242) and win on the split-stream residual GEMM with a long main loop, where staging writes + TMA-store reads
+    // compete with the operand traffic for the shared-memory pipe (fc2, K = 3072: 212 vs 219 us, same-call A/B) — that
+    // case is the default; MT_B200_EPI_DIRECT=1 / 0 forces direct / staged everywhere (A/B runs).
+    static int direct = -2;
+    if (direct == -2) {
       const char* e = getenv("MT_B200_EPI_DIRECT");
-      direct = (e && e[0] == '1') ? 1 : 0;
+      direct = !e ? -1 : (e[0] == '1' ? 1 : 0);
     }
-    const bool ok = direct && c.out_f32 == nullptr && (reinterpret_cast<uintptr_t>(c.y) & 31) == 0 &&
+    const bool want = direct == 1 || (direct == -1 && kHiLo && CG == 2 && K >= 2048);
+    const bool ok = want && c.out_f32 == nullptr && (reinterpret_cast<uintptr_t>(c.y) & 31) == 0 &&
                     (reinterpret_cast<uintptr_t>(c.y_lo) & 31) == 0 && (N % 16) == 0;
     p.y_direct = ok ? reinterpret_cast<__nv_bfloat16*>(c.y) : nullptr;
     p.ylo_direct = ok ? reinterpret_cast<__nv_bfloat16*>(c.y_lo) : nullptr;
